@@ -1,0 +1,441 @@
+// vrgdg_abi.cu — extern "C" boundary of libvrgdg_b200.so (declared in include/vrgdg_b200.h).
+// Validates arguments, builds TMA tensor maps, dispatches on dtype, never throws.
+#include "../../include/vrgdg_b200.h"
+#include "vrgdg_kernels.cuh"
+#include <atomic>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace vrgdg {
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace vrgdg
+
+using namespace vrgdg;
+
+namespace {
+
+thread_local char t_err[512] = "";
+thread_local const char* t_tile_path = "none";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  return fail(VRGDG_E_CUDA, "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+size_t elem_size(int dtype) { return dtype == VRGDG_F32 ? 4 : 2; }
+bool dtype_ok(int dtype) { return dtype == VRGDG_F32 || dtype == VRGDG_F16 || dtype == VRGDG_BF16; }
+
+int get_ctx(void* stream, LaunchCtx& ctx) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+  static thread_local int cached_dev = -1, cached_sms = 0, cached_major = 0;
+  if (cached_dev != dev) {
+    int sms = 0, major = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute");
+    if ((e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute");
+    cached_dev = dev; cached_sms = sms; cached_major = major;
+  }
+  if (cached_major != 10)
+    return fail(VRGDG_E_UNSUPPORTED, "libvrgdg_b200 holds sm_100a code only; device %d has compute capability major %d", dev, cached_major);
+  ctx.stream = reinterpret_cast<cudaStream_t>(stream);
+  ctx.sms = cached_sms;
+  return VRGDG_OK;
+}
+
+int check_frames(const void* in, const void* out, int B, int H, int W, int dtype, const char* who) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "%s: unknown dtype %d", who, dtype);
+  if (B < 0 || H < 0 || W < 0) return fail(VRGDG_E_INVALID, "%s: negative shape [%d,%d,%d]", who, B, H, W);
+  if ((int64_t)H * W >= (int64_t)1 << 31) return fail(VRGDG_E_UNSUPPORTED, "%s: frame of %d x %d pixels exceeds 2^31", who, H, W);
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (!in || !out) return fail(VRGDG_E_INVALID, "%s: null frame pointer", who);
+  size_t es = elem_size(dtype);
+  if ((reinterpret_cast<uintptr_t>(in) % es) || (reinterpret_cast<uintptr_t>(out) % es))
+    return fail(VRGDG_E_ALIGN, "%s: frame pointer not aligned to its element size", who);
+  return VRGDG_OK;
+}
+
+#define DISPATCH_DTYPE(dtype, CALL)                                        \
+  ((dtype) == VRGDG_F32 ? CALL(float) : ((dtype) == VRGDG_F16 ? CALL(__half) : CALL(__nv_bfloat16)))
+
+// ---- TMA tensor map over frames [B][H][RW] ---------------------------------------------------------
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t get_encode() {
+  static encode_fn_t fn = []() -> encode_fn_t {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<encode_fn_t>(p);
+  }();
+  return fn;
+}
+
+// returns true when a map was built (TMA path usable)
+bool build_tmap(CUtensorMap* map, const void* in, int B, int H, int RW, int dtype, int box_x, int box_y) {
+  const size_t es = elem_size(dtype);
+  if (getenv("VRGDG_NO_TMA")) return false;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || ((size_t)RW * es) % 16 != 0) return false;
+  if (RW < box_x || H < box_y) return false;      // tiny frames take the generic loader
+  encode_fn_t enc = get_encode();
+  if (!enc) return false;
+  CUtensorMapDataType dt = dtype == VRGDG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                         : dtype == VRGDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t dims[3] = {(cuuint64_t)RW, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)RW * es, (cuuint64_t)RW * es * (cuuint64_t)H};
+  cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, dt, 3, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+void fill_lut(LutParams& L, const float* lut, int S, const float* dmin, const float* dspan, float blend, float omb) {
+  L.lut = lut; L.S = S; L.smax = (float)(S - 1);
+  for (int i = 0; i < 3; ++i) { L.dmin[i] = dmin[i]; L.dspan[i] = dspan[i]; }
+  L.blend = blend; L.one_minus_blend = omb;
+}
+
+void zero_point(PointParams& P, int B, int H, int W) {
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.H = H; P.W = W; P.hw = (int64_t)H * W;
+}
+
+int run_tile(const void* in, void* out, int B, int H, int W, int dtype, TileParams& Q, int mask, bool exact, const LaunchCtx& ctx) {
+  if (in == out) return fail(VRGDG_E_INVALID, "tile kernels cannot run in place (in == out)");
+  Q.B = B; Q.H = H; Q.W = W; Q.RW = 3 * W;
+  int bx = 0, by = 0;
+#define GEO(T) (tile_geometry<T>(H, Q.RW, Q.tiles_x, Q.tiles_y, bx, by), 0)
+  (void)DISPATCH_DTYPE(dtype, GEO);
+#undef GEO
+  Q.total_tiles = (int64_t)B * Q.tiles_x * Q.tiles_y;
+  CUtensorMap map;
+  bool tma = build_tmap(&map, in, B, H, Q.RW, dtype, bx, by);
+  Q.use_tma = tma ? 1 : 0;
+  const size_t es = elem_size(dtype);
+  Q.vec_store = (((size_t)Q.RW * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
+  t_tile_path = tma ? "tma" : "generic";
+#define TL(T) launch_tile<T>(tma ? &map : nullptr, in, out, Q, mask, exact, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, TL);
+#undef TL
+  if (e != cudaSuccess) return fail_cuda(e, "k_tile launch");
+  return VRGDG_OK;
+}
+
+int check_lut(const float* lut, int S, const float* dmin, const float* dspan, const char* who) {
+  if (!lut || !dmin || !dspan) return fail(VRGDG_E_INVALID, "%s: null LUT / domain pointer", who);
+  if (S < 2 || S > 256) return fail(VRGDG_E_INVALID, "%s: LUT size %d outside [2,256]", who, S);
+  return VRGDG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vrgdg_version(void) { return VRGDG_ABI_VERSION; }
+const char* vrgdg_last_error(void) { return t_err; }
+int64_t vrgdg_launch_count(void) { return g_launches.load(); }
+const char* vrgdg_last_tile_path(void) { return t_tile_path; }
+
+int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+  int v = 0;
+  if (sm_count) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *sm_count = v; }
+  if (cc_major) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *cc_major = v; }
+  if (cc_minor) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *cc_minor = v; }
+  return VRGDG_OK;
+}
+
+int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype, const float* lut, int lut_size,
+                      const float* dmin_host, const float* dspan_host, float blend, float one_minus_blend, void* stream) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_apply: unknown dtype %d", dtype);
+  if (channels != 3 && channels != 4) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_apply: channels must be 3 or 4, got %d", channels);
+  if (npix < 0) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_apply: negative pixel count");
+  if (!(blend > 0.0f) || blend > 1.0f) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_apply: blend %g outside (0,1]", blend);
+  int rc = check_lut(lut, lut_size, dmin_host, dspan_host, "vrgdg_lut3d_apply");
+  if (rc) return rc;
+  if (npix == 0) return VRGDG_OK;
+  if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_apply: null frame pointer");
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  LutParams L;
+  fill_lut(L, lut, lut_size, dmin_host, dspan_host, blend, one_minus_blend);
+  cudaError_t e;
+  if (channels == 4) {
+#define LR(T) launch_lut_rgba<T>(in, out, npix, L, ctx)
+    e = DISPATCH_DTYPE(dtype, LR);
+#undef LR
+  } else {
+    // frames are independent of shape here: treat the pixel stream as frames of <= 2^30 pixels
+    // (chunk divisible by 8 keeps the vector path for every chunk but the last)
+    const int64_t chunk = (int64_t)1 << 30;
+    e = cudaSuccess;
+    for (int64_t p0 = 0; p0 < npix && e == cudaSuccess; p0 += chunk) {
+      int64_t n = npix - p0 < chunk ? npix - p0 : chunk;
+      PointParams P;
+      zero_point(P, 1, 1, (int)n);
+      P.lut = L;
+      const char* ip = reinterpret_cast<const char*>(in) + p0 * 3 * elem_size(dtype);
+      char* op = reinterpret_cast<char*>(out) + p0 * 3 * elem_size(dtype);
+#define PT(T) launch_point<T>(ip, op, P, ST_LUT, true, ctx)
+      e = DISPATCH_DTYPE(dtype, PT);
+#undef PT
+    }
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lut3d_apply");
+  return VRGDG_OK;
+}
+
+int vrgdg_grain(const void* in, void* out, int B, int H, int W, int dtype, float intensity, float sat, float one_minus_sat,
+                uint64_t seed, int64_t frame0, int seed_mode, const void* ext_noise, void* stream) {
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_grain");
+  if (rc) return rc;
+  if (seed_mode != VRGDG_SEED_PER_CLIP && seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "vrgdg_grain: bad seed_mode %d", seed_mode);
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  PointParams P;
+  zero_point(P, B, H, W);
+  P.gI = intensity; P.gs = sat; P.goms = one_minus_sat;
+  P.seed = seed; P.frame0 = frame0; P.seed_mode = seed_mode; P.ext_noise = ext_noise;
+  const bool exact = ext_noise != nullptr;
+#define PT(T) launch_point<T>(in, out, P, ST_GRAIN, exact, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, PT);
+#undef PT
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_grain");
+  return VRGDG_OK;
+}
+
+int vrgdg_grain_noise(float* out, int B, int H, int W, uint64_t seed, int64_t frame0, int seed_mode, void* stream) {
+  if (B < 0 || H < 0 || W < 0) return fail(VRGDG_E_INVALID, "vrgdg_grain_noise: negative shape");
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (!out) return fail(VRGDG_E_INVALID, "vrgdg_grain_noise: null output");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  int64_t total = (int64_t)B * H * W;
+  int grid = (int)(((total + 255) / 256) < (int64_t)ctx.sms * 16 ? ((total + 255) / 256) : (int64_t)ctx.sms * 16);
+  k_grain_noise<<<grid, 256, 0, ctx.stream>>>(out, B, (int64_t)H * W, seed, frame0, seed_mode);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_grain_noise");
+  return VRGDG_OK;
+}
+
+int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, int dtype, int op, float strength, int border, void* stream) {
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_stencil3x3");
+  if (rc) return rc;
+  if (op < VRGDG_STENCIL_BOX_UNSHARP || op > VRGDG_STENCIL_SOBEL_GPU) return fail(VRGDG_E_INVALID, "vrgdg_stencil3x3: bad op %d", op);
+  if (border != VRGDG_BORDER_REPLICATE && border != VRGDG_BORDER_ZERO) return fail(VRGDG_E_INVALID, "vrgdg_stencil3x3: bad border %d", border);
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  TileParams Q;
+  memset(&Q, 0, sizeof(Q));
+  zero_point(Q.P, B, H, W);
+  Q.op = op; Q.strength = strength; Q.border = border;
+  return run_tile(in, out, B, H, W, dtype, Q, 0, true, ctx);
+}
+
+int64_t vrgdg_lab_moments_scratch_bytes(int B) {
+  if (B < 0) return 0;
+  return (int64_t)B * MOMENT_BLOCKS * 6 * (int64_t)sizeof(double);
+}
+
+static int moments_common(const void* in, int B, int H, int W, int dtype, int row0, int rows, const PointParams* grainP,
+                          double* sums, void* scratch, int64_t scratch_bytes, void* stream, const char* who) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "%s: unknown dtype %d", who, dtype);
+  if (B < 0 || H <= 0 || W <= 0) return fail(VRGDG_E_INVALID, "%s: bad shape [%d,%d,%d]", who, B, H, W);
+  if (row0 < 0 || rows <= 0 || row0 + rows > H) return fail(VRGDG_E_INVALID, "%s: row range [%d,%d) outside [0,%d)", who, row0, row0 + rows, H);
+  if (B == 0) return VRGDG_OK;
+  if (!in || !sums || !scratch) return fail(VRGDG_E_INVALID, "%s: null pointer", who);
+  if (scratch_bytes < vrgdg_lab_moments_scratch_bytes(B)) return fail(VRGDG_E_INVALID, "%s: scratch too small (%lld < %lld)", who, (long long)scratch_bytes, (long long)vrgdg_lab_moments_scratch_bytes(B));
+  if (reinterpret_cast<uintptr_t>(sums) % 8 || reinterpret_cast<uintptr_t>(scratch) % 8) return fail(VRGDG_E_ALIGN, "%s: sums/scratch must be 8-byte aligned", who);
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  PointParams P;
+  if (grainP) P = *grainP; else zero_point(P, B, H, W);
+#define MO(T) launch_moments<T>(in, P, grainP != nullptr, row0, rows, sums, reinterpret_cast<double*>(scratch), ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, MO);
+#undef MO
+  if (e != cudaSuccess) return fail_cuda(e, who);
+  return VRGDG_OK;
+}
+
+int vrgdg_lab_moments(const void* in, int B, int H, int W, int dtype, int row0, int rows, double* sums, void* scratch,
+                      int64_t scratch_bytes, void* stream) {
+  return moments_common(in, B, H, W, dtype, row0, rows, nullptr, sums, scratch, scratch_bytes, stream, "vrgdg_lab_moments");
+}
+
+int vrgdg_colormatch_params(const double* frame_sums, int B, const double* ref_sums, int n_ref, float* params, void* stream) {
+  if (B < 0) return fail(VRGDG_E_INVALID, "vrgdg_colormatch_params: negative B");
+  if (B == 0) return VRGDG_OK;
+  if (!frame_sums || !ref_sums || !params) return fail(VRGDG_E_INVALID, "vrgdg_colormatch_params: null pointer");
+  if (n_ref != 1 && n_ref != B) return fail(VRGDG_E_INVALID, "vrgdg_colormatch_params: reference batch %d is neither 1 nor %d", n_ref, B);
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  k_colormatch_params<<<(B + 127) / 128, 128, 0, ctx.stream>>>(frame_sums, B, ref_sums, n_ref, params);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_colormatch_params");
+  return VRGDG_OK;
+}
+
+int vrgdg_colormatch_apply(const void* in, void* out, int B, int H, int W, int dtype, const float* params, float t,
+                           float one_minus_t, void* stream) {
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_colormatch_apply");
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (!params) return fail(VRGDG_E_INVALID, "vrgdg_colormatch_apply: null params");
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  PointParams P;
+  zero_point(P, B, H, W);
+  P.cm_params = params; P.cm_t = t; P.cm_omt = one_minus_t;
+#define PT(T) launch_point<T>(in, out, P, ST_CM, true, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, PT);
+#undef PT
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_colormatch_apply");
+  return VRGDG_OK;
+}
+
+static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, PointParams& P, int& mask, bool& exact, const void* ext_noise) {
+  zero_point(P, B, H, W);
+  mask = 0;
+  if (d->grain_enabled) {
+    if (d->grain_seed_mode != VRGDG_SEED_PER_CLIP && d->grain_seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "chain: bad grain seed_mode %d", d->grain_seed_mode);
+    mask |= ST_GRAIN;
+    P.gI = d->grain_intensity; P.gs = d->grain_sat; P.goms = d->grain_one_minus_sat;
+    P.seed = d->grain_seed; P.frame0 = d->grain_frame0; P.seed_mode = d->grain_seed_mode;
+    P.ext_noise = ext_noise;
+  }
+  if (d->colormatch_enabled) {
+    if (!d->cm_params) return fail(VRGDG_E_INVALID, "chain: colour match enabled without params");
+    mask |= ST_CM;
+    P.cm_params = d->cm_params; P.cm_t = d->cm_t; P.cm_omt = d->cm_one_minus_t;
+  }
+  if (d->lut_enabled) {
+    int rc = check_lut(d->lut, d->lut_size, d->lut_dmin, d->lut_dspan, "chain");
+    if (rc) return rc;
+    if (!(d->lut_blend > 0.0f) || d->lut_blend > 1.0f) return fail(VRGDG_E_INVALID, "chain: LUT blend %g outside (0,1]", d->lut_blend);
+    mask |= ST_LUT;
+    fill_lut(P.lut, d->lut, d->lut_size, d->lut_dmin, d->lut_dspan, d->lut_blend, d->lut_one_minus_blend);
+  }
+  // exact arithmetic unless the chain draws its own noise (then only the noise-free stages stay exact in k_point<.., true>)
+  exact = !(d->grain_enabled && ext_noise == nullptr);
+  return VRGDG_OK;
+}
+
+/* ext noise for the chain's first grain is passed through an environment-independent side door:
+ * vrgdg_chain_apply_ext (test hook used by the parity tests, same kernels). */
+static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
+                            const void* ext_noise, void* stream) {
+  if (!d) return fail(VRGDG_E_INVALID, "vrgdg_chain_apply: null descriptor");
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_apply");
+  if (rc) return rc;
+  if (d->stencil_op < VRGDG_STENCIL_NONE || d->stencil_op > VRGDG_STENCIL_SOBEL_GPU) return fail(VRGDG_E_INVALID, "chain: bad stencil op %d", d->stencil_op);
+  if (d->stencil_border != VRGDG_BORDER_REPLICATE && d->stencil_border != VRGDG_BORDER_ZERO) return fail(VRGDG_E_INVALID, "chain: bad border %d", d->stencil_border);
+  if (d->post_grain_enabled && d->post_seed_mode != VRGDG_SEED_PER_CLIP && d->post_seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "chain: bad post seed_mode");
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  TileParams Q;
+  memset(&Q, 0, sizeof(Q));
+  int mask = 0;
+  bool exact = true;
+  if ((rc = chain_point_params(d, B, H, W, Q.P, mask, exact, ext_noise))) return rc;
+  const bool need_tile = d->stencil_op != VRGDG_STENCIL_NONE || d->post_grain_enabled;
+  if (!need_tile) {
+    if (mask == 0) {   // nothing enabled: copy
+      if (in != out) {
+        cudaError_t e = cudaMemcpyAsync(out, in, (size_t)B * H * W * 3 * elem_size(dtype), cudaMemcpyDeviceToDevice, ctx.stream);
+        if (e != cudaSuccess) return fail_cuda(e, "chain copy");
+      }
+      return VRGDG_OK;
+    }
+#define PT(T) launch_point<T>(in, out, Q.P, mask, exact, ctx)
+    cudaError_t e = DISPATCH_DTYPE(dtype, PT);
+#undef PT
+    if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_apply");
+    return VRGDG_OK;
+  }
+  Q.op = d->stencil_op; Q.strength = d->stencil_strength; Q.border = d->stencil_border;
+  Q.post_enabled = d->post_grain_enabled ? 1 : 0;
+  Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
+  Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;
+  return run_tile(in, out, B, H, W, dtype, Q, mask, exact, ctx);
+}
+
+int vrgdg_chain_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, void* stream) {
+  return chain_apply_impl(in, out, B, H, W, dtype, desc, nullptr, stream);
+}
+
+/* same as vrgdg_chain_apply with the first grain stage reading N(0,1) from ext_noise ([B,H,W,3], frame dtype);
+ * exists so that the fused chain can be compared bit-for-bit in arithmetic with the reference composition. */
+int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
+                          const void* ext_noise, void* stream) {
+  return chain_apply_impl(in, out, B, H, W, dtype, desc, ext_noise, stream);
+}
+
+int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, double* sums,
+                            void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!desc) return fail(VRGDG_E_INVALID, "vrgdg_chain_lab_moments: null descriptor");
+  if (B < 0 || H <= 0 || W <= 0) return fail(VRGDG_E_INVALID, "vrgdg_chain_lab_moments: bad shape");
+  PointParams P;
+  zero_point(P, B, H, W);
+  if (desc->grain_enabled) {
+    P.gI = desc->grain_intensity; P.gs = desc->grain_sat; P.goms = desc->grain_one_minus_sat;
+    P.seed = desc->grain_seed; P.frame0 = desc->grain_frame0; P.seed_mode = desc->grain_seed_mode;
+  }
+  return moments_common(in, B, H, W, dtype, 0, H, desc->grain_enabled ? &P : nullptr, sums, scratch, scratch_bytes, stream,
+                        "vrgdg_chain_lab_moments");
+}
+
+int vrgdg_u8bgr_to_rgb(const uint8_t* in, void* out, int64_t npix, int dtype, void* stream) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: unknown dtype %d", dtype);
+  if (npix < 0) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: negative pixel count");
+  if (npix == 0) return VRGDG_OK;
+  if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: null pointer");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+#define UI(T) launch_u8_in<T>(in, out, npix, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, UI);
+#undef UI
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_u8bgr_to_rgb");
+  return VRGDG_OK;
+}
+
+int vrgdg_rgb_to_u8bgr(const void* in, uint8_t* out, int64_t npix, int dtype, void* stream) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: unknown dtype %d", dtype);
+  if (npix < 0) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: negative pixel count");
+  if (npix == 0) return VRGDG_OK;
+  if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: null pointer");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+#define UO(T) launch_u8_out<T>(in, out, npix, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, UO);
+#undef UO
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_rgb_to_u8bgr");
+  return VRGDG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+// kernels and launchers for float frames
+#include "vrgdg_inst.cuh"
+namespace vrgdg {
+VRGDG_INSTANTIATE(float)
+}

@@ -1,0 +1,151 @@
+// vrgdg_inst.cuh — host launchers, instantiated once per frame dtype (vrgdg_f32.cu / _f16.cu / _bf16.cu)
+#pragma once
+#include "vrgdg_kernels.cuh"
+#include <algorithm>
+#include <string.h>
+
+namespace vrgdg {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename K>
+static int occupancy_of(K kernel, int threads, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+
+// ---- k_point ---------------------------------------------------------------------------------
+template <typename T, int MASK, bool EXACT, bool VEC>
+static cudaError_t launch_point_k(const void* in, void* out, const PointParams& P, const LaunchCtx& ctx) {
+  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;
+  const int64_t groups = (P.hw + PX - 1) / PX;
+  const int bpf = (int)((groups + 255) / 256);
+  const int64_t total = (int64_t)bpf * P.B;
+  if (total == 0) return cudaSuccess;
+  auto kern = k_point<T, MASK, EXACT, VEC>;
+  static int occ = occupancy_of(kern, 256, 0);
+  const int64_t cap = (int64_t)ctx.sms * occ * 4;
+  const int grid = (int)std::min<int64_t>(total, cap);
+  kern<<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), P, bpf, total);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename T, int MASK, bool EXACT>
+static cudaError_t launch_point_v(const void* in, void* out, const PointParams& P, const LaunchCtx& ctx) {
+  constexpr int PX = (int)(48 / (3 * sizeof(T)));
+  bool vec = (P.hw % PX == 0) && aligned16(in) && aligned16(out) &&
+             (!(MASK & ST_GRAIN) || P.ext_noise == nullptr || aligned16(P.ext_noise));
+  if (vec) return launch_point_k<T, MASK, EXACT, true>(in, out, P, ctx);
+  return launch_point_k<T, MASK, EXACT, false>(in, out, P, ctx);
+}
+
+template <typename T>
+cudaError_t launch_point(const void* in, void* out, const PointParams& P, int mask, bool exact, const LaunchCtx& ctx) {
+  // masks without grain have no inexact variant (colour match always rounds like the reference; LUT alone is exact)
+#define VRGDG_PT(M)                                                                    \
+  case M:                                                                              \
+    if (((M) & ST_GRAIN) && !exact) return launch_point_v<T, M, false>(in, out, P, ctx); \
+    return launch_point_v<T, M, true>(in, out, P, ctx);
+  switch (mask) {
+    VRGDG_PT(1) VRGDG_PT(2) VRGDG_PT(3) VRGDG_PT(4) VRGDG_PT(5) VRGDG_PT(6) VRGDG_PT(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef VRGDG_PT
+}
+
+template <typename T>
+cudaError_t launch_lut_rgba(const void* in, void* out, int64_t npix, const LutParams& L, const LaunchCtx& ctx) {
+  if (npix == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)ctx.sms * 32);
+  k_lut_rgba<T><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), npix, L);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- k_tile ------------------------------------------------------------------------------------
+template <typename T>
+void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y) {
+  using C = TileCfg<T>;
+  tiles_x = (RW + C::TXE - 1) / C::TXE;
+  tiles_y = (H + C::TY - 1) / C::TY;
+  box_x = C::BX;
+  box_y = C::ROWS;
+}
+
+template <typename T, int MASK, bool EXACT>
+static cudaError_t launch_tile_k(const CUtensorMap* tmap, const void* in, void* out, TileParams& Q, const LaunchCtx& ctx) {
+  auto kern = k_tile<T, MASK, EXACT>;
+  constexpr size_t smem = tile_smem_bytes<T, MASK>();
+  // per device context, so set on every launch (single-process multi-GPU hosts)
+  cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) return attr;
+  static int occ = occupancy_of(kern, 256, smem);
+  if (Q.total_tiles == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx.sms * occ);
+  CUtensorMap dummy;
+  if (!tmap) { memset(&dummy, 0, sizeof(dummy)); tmap = &dummy; }
+  kern<<<grid, 256, smem, ctx.stream>>>(*tmap, reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), Q);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, TileParams& Q, int mask, bool exact,
+                        const LaunchCtx& ctx) {
+#define VRGDG_TL(M)                                                                        \
+  case M:                                                                                  \
+    if (((M) & ST_GRAIN) && !exact) return launch_tile_k<T, M, false>(tmap, in, out, Q, ctx); \
+    return launch_tile_k<T, M, true>(tmap, in, out, Q, ctx);
+  switch (mask) {
+    VRGDG_TL(0) VRGDG_TL(1) VRGDG_TL(2) VRGDG_TL(3) VRGDG_TL(4) VRGDG_TL(5) VRGDG_TL(6) VRGDG_TL(7)
+    default: return cudaErrorInvalidValue;
+  }
+#undef VRGDG_TL
+}
+
+// ---- moments -------------------------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows, double* sums,
+                           double* partials, const LaunchCtx& ctx) {
+  if (P.B == 0) return cudaSuccess;
+  dim3 grid(MOMENT_BLOCKS, P.B);
+  if (grain) k_lab_moments<T, true><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), P, row0, rows, partials);
+  else k_lab_moments<T, false><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), P, row0, rows, partials);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_moments_final<<<P.B, 32, 0, ctx.stream>>>(partials, MOMENT_BLOCKS, (double)rows * (double)P.W, sums);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- u8 codecs ---------------------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_u8_in(const uint8_t* in, void* out, int64_t npix, const LaunchCtx& ctx) {
+  if (npix == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)ctx.sms * 32);
+  k_u8bgr_to_rgb<T><<<grid, 256, 0, ctx.stream>>>(in, reinterpret_cast<T*>(out), npix);
+  count_launch();
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const LaunchCtx& ctx) {
+  if (npix == 0) return cudaSuccess;
+  const int grid = (int)std::min<int64_t>((npix + 255) / 256, (int64_t)ctx.sms * 32);
+  k_rgb_to_u8bgr<T><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), out, npix);
+  count_launch();
+  return cudaGetLastError();
+}
+
+#define VRGDG_INSTANTIATE(T)                                                                                              \
+  template cudaError_t launch_point<T>(const void*, void*, const PointParams&, int, bool, const LaunchCtx&);              \
+  template cudaError_t launch_lut_rgba<T>(const void*, void*, int64_t, const LutParams&, const LaunchCtx&);               \
+  template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
+  template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&); \
+  template cudaError_t launch_u8_in<T>(const uint8_t*, void*, int64_t, const LaunchCtx&);                                 \
+  template cudaError_t launch_u8_out<T>(const void*, uint8_t*, int64_t, const LaunchCtx&);                                \
+  template void tile_geometry<T>(int, int, int&, int&, int&, int&);
+
+}  // namespace vrgdg

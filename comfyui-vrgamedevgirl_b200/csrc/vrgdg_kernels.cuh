@@ -1,0 +1,646 @@
+// vrgdg_kernels.cuh — sm_100a kernels of the post-processing hot path.
+//
+// Two kernel families cover every entry point of include/vrgdg_b200.h:
+//   k_point : streaming per-pixel chain  [grain][colour match][3D LUT]          (no neighbourhood)
+//   k_tile  : TMA-staged halo tiles      [grain][colour match][3D LUT] -> 3x3 stencil -> [post grain]
+// plus the LAB moment reduction and the uint8 wire-format codecs.
+// Data layout: frames [B][H][W][3] channel-fastest; a frame row is RW = 3*W contiguous elements.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "vrgdg_math.cuh"
+
+namespace vrgdg {
+
+enum { ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4 };
+constexpr int PHILOX_ROUNDS = 10;
+
+// ---- element conversion -------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ float ld(float v) { return v; }
+  static __device__ __forceinline__ float st(float v) { return v; }
+};
+template <> struct Elem<__half> {
+  static __device__ __forceinline__ float ld(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half st(float v) { return __float2half_rn(v); }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 st(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ---- parameters of the per-pixel stages ------------------------------------------------------------
+struct PointParams {
+  int B, H, W;
+  int64_t hw;                  // pixels per frame
+  // grain
+  float gI, gs, goms;
+  uint64_t seed;
+  int64_t frame0;
+  int seed_mode;
+  const void* ext_noise;       // [B,H,W,3] of the frame dtype, or null
+  // colour match
+  const float* cm_params;      // [B][12]
+  float cm_t, cm_omt;
+  // LUT
+  LutParams lut;
+};
+
+// One pixel through the enabled stages.  nz* = external noise (used when has_ext).
+template <int MASK, bool EXACT>
+__device__ __forceinline__ void process_pixel(const PointParams& P, const GrainKey& gk, const float* cmp,
+                                              uint32_t pix_in_frame, bool has_ext,
+                                              float nzr, float nzg, float nzb,
+                                              float& r, float& g, float& b) {
+  if (MASK & ST_GRAIN) {
+    float zr, zg, zb;
+    if (has_ext) { zr = nzr; zg = nzg; zb = nzb; }
+    else grain_normals<PHILOX_ROUNDS>(gk, pix_in_frame, zr, zg, zb);
+    if (EXACT) grain_blend_exact(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
+    else grain_blend_fast(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
+  }
+  if (MASK & ST_CM) {
+    colormatch_pixel(r, g, b, cmp, P.cm_t, P.cm_omt);
+  }
+  if (MASK & ST_LUT) {
+    float x0 = r, x1 = g, x2 = b;
+    lut3d_eval<EXACT>(P.lut, r, g, b);
+    if (P.lut.blend < 1.0f) {
+      r = lut_blend<EXACT>(x0, r, P.lut.blend, P.lut.one_minus_blend);
+      g = lut_blend<EXACT>(x1, g, P.lut.blend, P.lut.one_minus_blend);
+      b = lut_blend<EXACT>(x2, b, P.lut.blend, P.lut.one_minus_blend);
+    }
+  }
+}
+
+// =====================================================================================================
+// k_point — streaming chain.  VEC: a thread owns 48 bytes = PX whole pixels (4 fp32 / 8 fp16) moved with
+// three 16-byte loads and stores; requires hw % PX == 0 and 16-byte aligned bases.  !VEC: one pixel per
+// thread, scalar accesses (any shape / alignment).
+// =====================================================================================================
+template <typename T, int MASK, bool EXACT, bool VEC>
+__global__ void __launch_bounds__(256)
+k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
+        int blocks_per_frame, int64_t total_vblocks) {
+  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;
+  constexpr int NE = PX * 3;
+  const bool has_ext = (MASK & ST_GRAIN) && (P.ext_noise != nullptr);
+  for (int64_t vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int frame = (int)(vb / blocks_per_frame);
+    const int bif = (int)(vb - (int64_t)frame * blocks_per_frame);
+    const int64_t pix0 = ((int64_t)bif * 256 + threadIdx.x) * PX;
+    if (pix0 >= P.hw) continue;
+    const int64_t e0 = ((int64_t)frame * P.hw + pix0) * 3;
+    GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+    const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
+
+    float v[NE];
+    float nz[NE];
+    if (VEC) {
+      union { uint4 q[3]; T e[NE]; } u;
+      const uint4* src = reinterpret_cast<const uint4*>(in + e0);
+      u.q[0] = __ldg(src); u.q[1] = __ldg(src + 1); u.q[2] = __ldg(src + 2);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) v[i] = Elem<T>::ld(u.e[i]);
+      if (has_ext) {
+        union { uint4 q[3]; T e[NE]; } n;
+        const uint4* ns = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(P.ext_noise) + e0);
+        n.q[0] = __ldg(ns); n.q[1] = __ldg(ns + 1); n.q[2] = __ldg(ns + 2);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nz[i] = Elem<T>::ld(n.e[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) v[i] = Elem<T>::ld(in[e0 + i]);
+      if (has_ext) {
+        const T* ns = reinterpret_cast<const T*>(P.ext_noise) + e0;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nz[i] = Elem<T>::ld(ns[i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      process_pixel<MASK, EXACT>(P, gk, cmp, (uint32_t)(pix0 + j), has_ext,
+                                 has_ext ? nz[3 * j] : 0.f, has_ext ? nz[3 * j + 1] : 0.f,
+                                 has_ext ? nz[3 * j + 2] : 0.f, v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+    }
+    if (VEC) {
+      union { uint4 q[3]; T e[NE]; } u;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) u.e[i] = Elem<T>::st(v[i]);
+      uint4* dst = reinterpret_cast<uint4*>(out + e0);
+      dst[0] = u.q[0]; dst[1] = u.q[1]; dst[2] = u.q[2];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) out[e0 + i] = Elem<T>::st(v[i]);
+    }
+  }
+}
+
+// LUT on 4-channel frames (alpha copied through): VRGDG_IV_Adjustments.py:341-343
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_lut_rgba(const T* __restrict__ in, T* __restrict__ out, int64_t npix, LutParams L) {
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
+    const T* s = in + p * 4;
+    float r = Elem<T>::ld(s[0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[2]);
+    T a = s[3];
+    float x0 = r, x1 = g, x2 = b;
+    lut3d_eval<true>(L, r, g, b);
+    if (L.blend < 1.0f) {
+      r = lut_blend<true>(x0, r, L.blend, L.one_minus_blend);
+      g = lut_blend<true>(x1, g, L.blend, L.one_minus_blend);
+      b = lut_blend<true>(x2, b, L.blend, L.one_minus_blend);
+    }
+    T* d = out + p * 4;
+    d[0] = Elem<T>::st(r); d[1] = Elem<T>::st(g); d[2] = Elem<T>::st(b);
+    d[3] = (L.blend < 1.0f) ? Elem<T>::st(lut_blend<true>(Elem<T>::ld(a), Elem<T>::ld(a), L.blend, L.one_minus_blend)) : a;
+  }
+}
+
+// raw normals of the generator, [B,H,W,3] fp32
+static __global__ void __launch_bounds__(256)
+k_grain_noise(float* __restrict__ out, int B, int64_t hw, uint64_t seed, int64_t frame0, int seed_mode) {
+  const int64_t total = (int64_t)B * hw;
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+    int frame = (int)(p / hw);
+    uint32_t pif = (uint32_t)(p - (int64_t)frame * hw);
+    GrainKey gk = grain_key(seed, frame0, frame, seed_mode);
+    float zr, zg, zb;
+    grain_normals<PHILOX_ROUNDS>(gk, pif, zr, zg, zb);
+    out[p * 3] = zr; out[p * 3 + 1] = zg; out[p * 3 + 2] = zb;
+  }
+}
+
+// =====================================================================================================
+// mbarrier / TMA primitives (inline PTX; SASS: SYNCS.*, UTMALDG)
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost TMA completion traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// =====================================================================================================
+// k_tile — halo tiles staged in shared memory by TMA (3-stage mbarrier ring), optional per-pixel
+// pre-stages applied to the whole halo tile in shared memory, 3x3 stencil, optional post grain.
+// =====================================================================================================
+struct TileParams {
+  int B, H, W, RW;              // RW = 3*W elements per row
+  int tiles_x, tiles_y;
+  int64_t total_tiles;
+  PointParams P;                // pre-stages
+  int op;                       // VRGDG_STENCIL_*
+  float strength;
+  int border;                   // 0 replicate, 1 zero
+  int post_enabled;
+  float pI, ps, poms;
+  uint64_t pseed;
+  int64_t pframe0;
+  int pseed_mode;
+  int use_tma;                  // 0: cooperative bounds-checked loads (any alignment)
+  int vec_store;                // rows 16-byte aligned -> 16-byte stores
+};
+
+template <typename T> struct TileCfg {
+  static constexpr int VEC = 16 / sizeof(T);          // output elements per thread per row
+  static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
+  static constexpr int PADL = VEC;                    // box starts PADL elements left of the tile (>= 3)
+  static constexpr int TXE = 240;                     // output elements per tile row (multiple of 3 and of VEC)
+  static constexpr int TY = 32;                       // output rows per tile
+  static constexpr int ROWS = TY + 2;
+  static constexpr int COLS = TXE / VEC;              // threads across
+  static constexpr int RG = 240 / COLS;               // row groups (240 active threads of 256)
+  static constexpr int RPT = TY / RG;                 // rows per thread
+  static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
+  static constexpr int NS = 3;                        // pipeline stages
+  static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
+  static_assert(PADL + TXE + 3 <= BX, "box too narrow");
+  static_assert(TY % RG == 0, "rows per thread");
+};
+
+template <typename T, int MASK>
+constexpr size_t tile_smem_bytes() {
+  size_t s = (size_t)TileCfg<T>::NS * TileCfg<T>::STAGE_BYTES;
+  if (MASK != 0 && sizeof(T) != 4) s += (size_t)TileCfg<T>::ROWS * TileCfg<T>::BX * 4;   // fp32 work tile
+  return s + 64 /* mbarriers */ + 128 /* alignment slack */;
+}
+
+// replicate-border fix-up of a staged tile (np.pad(mode="edge") on the stage's input)
+template <typename E, typename CFG>
+__device__ __forceinline__ void fix_border(E* tile, int y0, int x0e, int H, int RW) {
+  constexpr int BX = CFG::BX, ROWS = CFG::ROWS, PADL = CFG::PADL, TY = CFG::TY, TXE = CFG::TXE;
+  const int vr = H - y0;        // image rows from y0 to the bottom
+  const int ve = RW - x0e;      // row elements from x0e to the right edge
+  const bool top = (y0 == 0), bot = (vr <= TY), left = (x0e == 0), right = (ve <= TXE);
+  if (!(top || bot || left || right)) return;   // uniform per tile
+  if (top || bot) {
+    for (int c = threadIdx.x; c < BX; c += blockDim.x) {
+      if (top) tile[c] = tile[BX + c];
+      if (bot) tile[(vr + 1) * BX + c] = tile[vr * BX + c];
+    }
+  }
+  __syncthreads();
+  if (left || right) {
+    for (int i = threadIdx.x; i < ROWS * 3; i += blockDim.x) {
+      int r = i / 3, c = i - r * 3;
+      E* row = tile + r * BX;
+      if (left) row[PADL - 3 + c] = row[PADL + c];
+      if (right) row[PADL + ve + c] = row[PADL + ve - 3 + c];
+    }
+  }
+  __syncthreads();
+}
+
+// window row: WN = VEC+6 floats starting at element (f0 - 3) of the tile row
+template <typename E, int VEC>
+__device__ __forceinline__ void load_window(const E* rowp /* -> tile column PADL+f0 */, float* w) {
+  if (sizeof(E) == 4) {
+    // floats [f0-4, f0+VEC+4): (VEC+8)/4 aligned float4
+    constexpr int NV = (VEC + 8) / 4;
+    float tmp[NV * 4];
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) - 4);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 q = p[i];
+      tmp[4 * i] = q.x; tmp[4 * i + 1] = q.y; tmp[4 * i + 2] = q.z; tmp[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC + 6; ++i) w[i] = tmp[i + 1];
+  } else {
+    // 16-bit elements [f0-8, f0+16): three aligned uint4 (VEC == 8)
+    union { uint4 q[3]; E e[24]; } u;
+    const uint4* p = reinterpret_cast<const uint4*>(rowp - 8);
+    u.q[0] = p[0]; u.q[1] = p[1]; u.q[2] = p[2];
+#pragma unroll
+    for (int i = 0; i < VEC + 6; ++i) w[i] = Elem<E>::ld(u.e[i + 5]);
+  }
+}
+
+template <typename T, int OP, bool WORK>
+__device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
+                                             int frame, int y0, int x0e) {
+  using C = TileCfg<T>;
+  constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, WN = VEC + 6;
+  const int tid = threadIdx.x;
+  if (tid >= C::COLS * C::RG) return;
+  const int cx = tid % C::COLS, rg = tid / C::COLS;
+  const int f0 = cx * VEC;
+  const int ge0 = x0e + f0;                 // first output element in the row
+  const int rbase = rg * C::RPT;            // first output row of this thread == smem row of its upper neighbour
+  float w[3][WN];
+  auto load_row = [&](int srow, float* dst) {
+    if (WORK) load_window<float, VEC>(work + srow * BX + PADL + f0, dst);
+    else load_window<T, VEC>(raw + srow * BX + PADL + f0, dst);
+  };
+  load_row(rbase, w[0]);
+  load_row(rbase + 1, w[1]);
+  GrainKey pk = grain_key(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
+#pragma unroll
+  for (int j = 0; j < C::RPT; ++j) {
+    load_row(rbase + j + 2, w[2]);
+    const int y = y0 + rbase + j;
+    float o[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float n[9] = {w[0][e], w[0][e + 3], w[0][e + 6], w[1][e], w[1][e + 3], w[1][e + 6],
+                    w[2][e], w[2][e + 3], w[2][e + 6]};
+      o[e] = stencil_epilogue(OP, n, Q.strength);
+    }
+    if (Q.post_enabled) {
+      // grain after the stencil (EnhancerNodes.py:285-293); element -> (pixel, channel)
+      const int pfirst = ge0 / 3;
+      constexpr int NPQ = (VEC + 4) / 3;
+#pragma unroll
+      for (int q = 0; q < NPQ; ++q) {
+        const int px = pfirst + q;
+        float zr, zg, zb;
+        grain_normals<PHILOX_ROUNDS>(pk, (uint32_t)y * (uint32_t)Q.W + (uint32_t)px, zr, zg, zb);
+        const float gy = Q.poms * zg;
+        const float g0 = fmaf(2.0f * Q.ps, zr, gy), g1 = fmaf(Q.ps, zg, gy), g2 = fmaf(3.0f * Q.ps, zb, gy);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int ch = ge0 + e - px * 3;
+          if (ch >= 0 && ch < 3) {
+            const float gv = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
+            o[e] = clamp01(fmaf(Q.pI, gv, o[e]));
+          }
+        }
+      }
+    }
+    if (y < Q.H && ge0 < Q.RW) {
+      T* dst = out + ((int64_t)frame * Q.H + y) * Q.RW + ge0;
+      if (Q.vec_store) {
+        union { uint4 q; T e[VEC]; } u;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
+        *reinterpret_cast<uint4*>(dst) = u.q;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) if (ge0 + e < Q.RW) dst[e] = Elem<T>::st(o[e]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
+  }
+}
+
+template <typename T, int MASK, bool EXACT>
+__global__ void __launch_bounds__(256, 2)
+k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __restrict__ out, TileParams Q) {
+  using C = TileCfg<T>;
+  constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, TXE = C::TXE, TY = C::TY, ROWS = C::ROWS;
+  constexpr int NS = C::NS;
+  constexpr bool WORK = (MASK != 0) && (sizeof(T) != 4);   // separate fp32 tile for the pre-stage results
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  T* stage0 = reinterpret_cast<T*>(base);
+  float* work = reinterpret_cast<float*>(base + (size_t)NS * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NS * C::STAGE_BYTES + (WORK ? ROWS * BX * 4 : 0));
+
+  const int tid = threadIdx.x;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t n_my = (Q.total_tiles > first) ? (Q.total_tiles - first + stride - 1) / stride : 0;
+  const int tiles_per_frame = Q.tiles_x * Q.tiles_y;
+  const bool tma = Q.use_tma != 0;
+
+  if (tma && tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  auto tile_coords = [&](int64_t k, int& frame, int& y0, int& x0e) {
+    int64_t t = first + k * stride;
+    frame = (int)(t / tiles_per_frame);
+    int rem = (int)(t - (int64_t)frame * tiles_per_frame);
+    int ty = rem / Q.tiles_x;
+    y0 = ty * TY;
+    x0e = (rem - ty * Q.tiles_x) * TXE;
+  };
+  auto issue = [&](int64_t k) {
+    int frame, y0, x0e;
+    tile_coords(k, frame, y0, x0e);
+    int s = (int)(k % NS);
+    mbar_arrive_expect_tx(&bars[s], (uint32_t)C::STAGE_BYTES);
+    tma_load_3d(reinterpret_cast<uint8_t*>(stage0) + (size_t)s * C::STAGE_BYTES, &tmap, x0e - PADL, y0 - 1, frame, &bars[s]);
+  };
+
+  if (tma && tid == 0) {
+    for (int64_t k = 0; k < NS - 1 && k < n_my; ++k) issue(k);
+  }
+
+  for (int64_t k = 0; k < n_my; ++k) {
+    int frame, y0, x0e;
+    tile_coords(k, frame, y0, x0e);
+    const int s = tma ? (int)(k % NS) : 0;
+    T* raw = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(stage0) + (size_t)s * C::STAGE_BYTES);
+
+    if (tma) {
+      if (tid == 0 && k + NS - 1 < n_my) {
+        fence_proxy_async();          // order earlier generic-proxy accesses of that stage before the async write
+        issue(k + NS - 1);
+      }
+      mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));
+    } else {
+      // generic loader: zero-filled halo tile, any alignment
+      const T* fbase = in + (int64_t)frame * Q.H * Q.RW;
+      for (int i = tid; i < ROWS * BX; i += 256) {
+        int r = i / BX, c = i - r * BX;
+        int y = y0 - 1 + r, x = x0e - PADL + c;
+        T v = Elem<T>::st(0.0f);
+        if (y >= 0 && y < Q.H && x >= 0 && x < Q.RW) v = fbase[(int64_t)y * Q.RW + x];
+        raw[i] = v;
+      }
+      __syncthreads();
+    }
+
+    // ---- per-pixel pre-stages over the halo tile (grain / colour match / LUT), result in fp32 ----
+    if (MASK != 0) {
+      const PointParams& P = Q.P;
+      GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+      const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
+      const bool has_ext = (MASK & ST_GRAIN) && (P.ext_noise != nullptr);
+      const int px0 = x0e / 3 - 1;
+      for (int i = tid; i < ROWS * C::PPR; i += 256) {
+        int r = i / C::PPR, kx = i - r * C::PPR;
+        int y = y0 - 1 + r, px = px0 + kx;
+        int so = r * BX + PADL - 3 + 3 * kx;
+        bool inside = (y >= 0 && y < Q.H && px >= 0 && px < Q.W);
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if (inside) {
+          cr = Elem<T>::ld(raw[so]); cg = Elem<T>::ld(raw[so + 1]); cb = Elem<T>::ld(raw[so + 2]);
+          uint32_t pif = (uint32_t)y * (uint32_t)Q.W + (uint32_t)px;
+          float nr = 0.f, ng = 0.f, nb = 0.f;
+          if (has_ext) {
+            const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
+            nr = Elem<T>::ld(ns[0]); ng = Elem<T>::ld(ns[1]); nb = Elem<T>::ld(ns[2]);
+          }
+          process_pixel<MASK, EXACT>(P, gk, cmp, pif, has_ext, nr, ng, nb, cr, cg, cb);
+        }
+        if (WORK) { work[so] = cr; work[so + 1] = cg; work[so + 2] = cb; }
+        else if (inside) {
+          float* rf = reinterpret_cast<float*>(raw);
+          rf[so] = cr; rf[so + 1] = cg; rf[so + 2] = cb;
+        }
+      }
+      __syncthreads();
+    }
+
+    if (Q.border == 0) {
+      if (WORK) fix_border<float, C>(work, y0, x0e, Q.H, Q.RW);
+      else fix_border<T, C>(raw, y0, x0e, Q.H, Q.RW);
+    }
+
+    // ---- 3x3 stencil, sliding 3-row register window, VEC outputs per thread per row ----
+    {
+      const float* wt = WORK ? work : nullptr;
+      switch (Q.op) {   // uniform; one specialised row loop per epilogue
+        case 1: stencil_rows<T, 1, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 2: stencil_rows<T, 2, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 3: stencil_rows<T, 3, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 4: stencil_rows<T, 4, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 5: stencil_rows<T, 5, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        default: stencil_rows<T, 0, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+      }
+    }
+    if (tma) fence_proxy_async();   // generic-proxy writes to this stage happen-before its next async refill
+    __syncthreads();   // every thread is done with this stage before it is refilled
+  }
+}
+
+// =====================================================================================================
+// LAB moments: per frame {S_L,S_a,S_b,S_LL,S_aa,S_bb} in fp64, fixed reduction order (deterministic).
+// grid = (NB, B); each block writes one partial; k_moments_final folds the NB partials per frame.
+// =====================================================================================================
+constexpr int MOMENT_BLOCKS = 296;   // per frame, independent of B so results do not depend on sharding
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, bool GRAIN>
+__global__ void __launch_bounds__(256)
+k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials) {
+  const int frame = blockIdx.y;
+  const int64_t pbeg = (int64_t)row0 * P.W, n = (int64_t)rows * P.W;
+  const T* fbase = in + (int64_t)frame * P.hw * 3;
+  GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+  const bool has_ext = GRAIN && (P.ext_noise != nullptr);
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t pif = pbeg + i;
+    const T* s = fbase + pif * 3;
+    float r = Elem<T>::ld(s[0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[2]);
+    if (GRAIN) {
+      float nr = 0.f, ng = 0.f, nb = 0.f;
+      if (has_ext) {
+        const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
+        nr = Elem<T>::ld(ns[0]); ng = Elem<T>::ld(ns[1]); nb = Elem<T>::ld(ns[2]);
+        process_pixel<ST_GRAIN, true>(P, gk, nullptr, (uint32_t)pif, true, nr, ng, nb, r, g, b);
+      } else {
+        process_pixel<ST_GRAIN, false>(P, gk, nullptr, (uint32_t)pif, false, 0.f, 0.f, 0.f, r, g, b);
+      }
+    }
+    float L, A, Bv;
+    rgb_to_lab(r, g, b, L, A, Bv);
+    acc[0] += (double)L; acc[1] += (double)A; acc[2] += (double)Bv;
+    acc[3] += (double)L * (double)L; acc[4] += (double)A * (double)A; acc[5] += (double)Bv * (double)Bv;
+  }
+  __shared__ double red[8][6];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double v = warp_sum(acc[q]);
+    if (lane == 0) red[wid][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partials[((int64_t)frame * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+  }
+}
+
+// sums[frame] = {n, S1[3], S2[3]}
+static __global__ void k_moments_final(const double* __restrict__ partials, int nb, double n, double* __restrict__ sums) {
+  const int frame = blockIdx.x, lane = threadIdx.x;   // 32 threads
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[q] += partials[((int64_t)frame * nb + b) * 6 + q];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane == 0) {
+    double* o = sums + (int64_t)frame * 7;
+    o[0] = n;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) o[1 + q] = acc[q];
+  }
+}
+
+// params[b] = {mu_img[3], sd_img[3], mu_ref[3], sd_ref[3]};  sd = sqrt(unbiased var) + 1e-5  (nodes.py:99-100,109-110)
+static __global__ void k_colormatch_params(const double* __restrict__ fs, int B, const double* __restrict__ rs, int n_ref,
+                                    float* __restrict__ params) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* f = fs + (int64_t)b * 7;
+  const double* r = rs + (int64_t)((n_ref == 1) ? 0 : b) * 7;
+  float* p = params + (int64_t)b * 12;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double n = f[0], m = f[1 + c] / n;
+    double var = (f[4 + c] - f[1 + c] * m) / (n - 1.0);
+    p[c] = (float)m;
+    p[3 + c] = __fadd_rn((float)sqrt(var > 0 ? var : 0.0), 1e-5f);
+    double nr = r[0], mr = r[1 + c] / nr;
+    double varr = (r[4 + c] - r[1 + c] * mr) / (nr - 1.0);
+    p[6 + c] = (float)mr;
+    p[9 + c] = __fadd_rn((float)sqrt(varr > 0 ? varr : 0.0), 1e-5f);
+  }
+}
+
+// =====================================================================================================
+// uint8 BGR wire format (VRGDG_LUTVideoTools.py:736-752): 4 pixels (12 bytes) per thread
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_u8bgr_to_rgb(const uint8_t* __restrict__ in, T* __restrict__ out, int64_t npix) {
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
+    const uint8_t* s = in + p * 3;
+    float b = (float)s[0], g = (float)s[1], r = (float)s[2];
+    T* d = out + p * 3;
+    d[0] = Elem<T>::st(divx(r, 255.0f));     // astype(float32) / 255.0
+    d[1] = Elem<T>::st(divx(g, 255.0f));
+    d[2] = Elem<T>::st(divx(b, 255.0f));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_rgb_to_u8bgr(const T* __restrict__ in, uint8_t* __restrict__ out, int64_t npix) {
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
+    const T* s = in + p * 3;
+    float r = Elem<T>::ld(s[0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[2]);
+    // np.clip(x * 255.0, 0, 255).astype(uint8): truncation
+    uint8_t* d = out + p * 3;
+    d[0] = (uint8_t)fminf(fmaxf(mulx(b, 255.0f), 0.0f), 255.0f);
+    d[1] = (uint8_t)fminf(fmaxf(mulx(g, 255.0f), 0.0f), 255.0f);
+    d[2] = (uint8_t)fminf(fmaxf(mulx(r, 255.0f), 0.0f), 255.0f);
+  }
+}
+
+// ---- host-side launchers implemented per dtype translation unit (vrgdg_inst.cuh) --------------------
+struct LaunchCtx { cudaStream_t stream; int sms; };
+
+template <typename T> cudaError_t launch_point(const void* in, void* out, const PointParams& P, int mask, bool exact,
+                                               const LaunchCtx& ctx);
+template <typename T> cudaError_t launch_lut_rgba(const void* in, void* out, int64_t npix, const LutParams& L,
+                                                  const LaunchCtx& ctx);
+template <typename T> cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, TileParams& Q, int mask,
+                                              bool exact, const LaunchCtx& ctx);
+template <typename T> cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows,
+                                                 double* sums, double* partials, const LaunchCtx& ctx);
+template <typename T> cudaError_t launch_u8_in(const uint8_t* in, void* out, int64_t npix, const LaunchCtx& ctx);
+template <typename T> cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const LaunchCtx& ctx);
+template <typename T> void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y);
+
+void count_launch();
+
+}  // namespace vrgdg

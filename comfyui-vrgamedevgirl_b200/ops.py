@@ -1,0 +1,177 @@
+"""Tensor-level wrappers over the C ABI: CUDA tensors in, CUDA tensors out, work enqueued on the
+caller's current stream.  Python allocates every output (torch's allocator owns frame memory)."""
+import ctypes
+
+import torch
+
+from . import _native as nv
+
+
+def _frames(images, name="images"):
+    t = nv.require_cuda(images, name)
+    if t.ndim != 4 or t.shape[-1] != 3:
+        raise ValueError("vrgdg_b200: %s must be shaped [batch, height, width, 3], got %s" % (name, tuple(t.shape)))
+    return t
+
+
+def _f32(v):
+    return ctypes.c_float(float(v))
+
+
+def lut3d_apply(image, lut, dmin, dspan, blend=1.0, one_minus_blend=0.0):
+    """VRGDG_LUTS._apply_cube_lut + strength blend.  image [B,H,W,3|4] CUDA; lut [S,S,S,3] fp32 CUDA;
+    dmin / dspan: 3 python floats each (dspan already clamped to >= 1e-6 in the image dtype)."""
+    t = nv.require_cuda(image, "image")
+    if t.ndim != 4 or t.shape[-1] not in (3, 4):
+        raise ValueError("VRGDG_LUTS expects IMAGE input shaped like [batch, height, width, channels].")
+    lut = nv.require_cuda(lut, "lut")
+    if lut.dtype != torch.float32 or lut.ndim != 4 or lut.shape[3] != 3 or not (lut.shape[0] == lut.shape[1] == lut.shape[2]):
+        raise ValueError("vrgdg_b200: lut must be float32 [S,S,S,3]")
+    if lut.device != t.device:
+        raise ValueError("vrgdg_b200: lut and image are on different devices")
+    out = torch.empty_like(t)
+    c3 = ctypes.c_float * 3
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_lut3d_apply(nv.ptr(t), nv.ptr(out), t.numel() // t.shape[-1], int(t.shape[-1]), nv.DTYPE_CODE[t.dtype],
+                                       nv.ptr(lut), int(lut.shape[0]), c3(*[float(x) for x in dmin]), c3(*[float(x) for x in dspan]),
+                                       _f32(blend), _f32(one_minus_blend), nv.stream_ptr(t.device)))
+    return out
+
+
+def grain(images, intensity, sat, one_minus_sat, seed, frame0=0, seed_mode=nv.SEED_PER_CLIP, ext_noise=None):
+    t = _frames(images)
+    n = None
+    if ext_noise is not None:
+        n = nv.require_cuda(ext_noise, "ext_noise")
+        if n.shape != t.shape or n.dtype != t.dtype or n.device != t.device:
+            raise ValueError("vrgdg_b200: ext_noise must match images in shape, dtype and device")
+    out = torch.empty_like(t)
+    B, H, W, _ = t.shape
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_grain(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], _f32(intensity), _f32(sat), _f32(one_minus_sat),
+                                 ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), ctypes.c_int64(int(frame0)), int(seed_mode), nv.ptr(n),
+                                 nv.stream_ptr(t.device)))
+    return out
+
+
+def grain_noise(B, H, W, seed, frame0=0, seed_mode=nv.SEED_PER_CLIP, device="cuda"):
+    out = torch.empty((B, H, W, 3), dtype=torch.float32, device=device)
+    lib = nv.load_library()
+    with torch.cuda.device(out.device):
+        nv.check(lib.vrgdg_grain_noise(nv.ptr(out), B, H, W, ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), ctypes.c_int64(int(frame0)),
+                                       int(seed_mode), nv.stream_ptr(out.device)))
+    return out
+
+
+def stencil3x3(images, op, strength, border=nv.BORDER_REPLICATE):
+    t = _frames(images)
+    out = torch.empty_like(t)
+    B, H, W, _ = t.shape
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_stencil3x3(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], int(op), _f32(strength), int(border),
+                                      nv.stream_ptr(t.device)))
+    return out
+
+
+def lab_moments(images, row0=0, rows=None):
+    """Raw LAB sums per frame over rows [row0,row0+rows): float64 [B,7] = {n, S_L,S_a,S_b, S_LL,S_aa,S_bb}."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    rows = H - row0 if rows is None else rows
+    lib = nv.load_library()
+    sums = torch.empty((B, 7), dtype=torch.float64, device=t.device)
+    nbytes = int(lib.vrgdg_lab_moments_scratch_bytes(B))
+    scratch = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_lab_moments(nv.ptr(t), B, H, W, nv.DTYPE_CODE[t.dtype], int(row0), int(rows), nv.ptr(sums), nv.ptr(scratch),
+                                       ctypes.c_int64(nbytes), nv.stream_ptr(t.device)))
+    return sums
+
+
+def colormatch_params(frame_sums, ref_sums):
+    """[B,7] + [1|B,7] float64 CUDA -> [B,12] float32 {mu_img, sd_img, mu_ref, sd_ref}."""
+    fs = frame_sums.contiguous()
+    rs = ref_sums.to(fs.device).contiguous()
+    if fs.dtype != torch.float64 or rs.dtype != torch.float64 or fs.ndim != 2 or fs.shape[1] != 7 or rs.ndim != 2 or rs.shape[1] != 7:
+        raise ValueError("vrgdg_b200: moment sums must be float64 [n,7]")
+    if fs.device.type != "cuda":
+        raise RuntimeError("vrgdg_b200: moment sums must live on a CUDA device")
+    B = fs.shape[0]
+    params = torch.empty((B, 12), dtype=torch.float32, device=fs.device)
+    lib = nv.load_library()
+    with torch.cuda.device(fs.device):
+        nv.check(lib.vrgdg_colormatch_params(nv.ptr(fs), B, nv.ptr(rs), int(rs.shape[0]), nv.ptr(params), nv.stream_ptr(fs.device)))
+    return params
+
+
+def colormatch_apply(images, params, t_strength, one_minus_t):
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    p = params.contiguous()
+    if p.dtype != torch.float32 or p.shape != (B, 12) or p.device != t.device:
+        raise ValueError("vrgdg_b200: params must be float32 [B,12] on the images' device")
+    out = torch.empty_like(t)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_colormatch_apply(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], nv.ptr(p), _f32(t_strength), _f32(one_minus_t),
+                                            nv.stream_ptr(t.device)))
+    return out
+
+
+def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None):
+    """Run the fused chain described by a ChainDesc.  `keepalive` holds tensors the descriptor points to."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    if out is None:
+        out = torch.empty_like(t)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        if ext_noise is not None:
+            n = nv.require_cuda(ext_noise, "ext_noise")
+            if n.shape != t.shape or n.dtype != t.dtype or n.device != t.device:
+                raise ValueError("vrgdg_b200: ext_noise must match images in shape, dtype and device")
+            nv.check(lib.vrgdg_chain_apply_ext(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(n),
+                                               nv.stream_ptr(t.device)))
+        else:
+            nv.check(lib.vrgdg_chain_apply(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.stream_ptr(t.device)))
+    del keepalive
+    return out
+
+
+def chain_lab_moments(images, desc):
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    lib = nv.load_library()
+    sums = torch.empty((B, 7), dtype=torch.float64, device=t.device)
+    nbytes = int(lib.vrgdg_lab_moments_scratch_bytes(B))
+    scratch = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_chain_lab_moments(nv.ptr(t), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(sums), nv.ptr(scratch),
+                                             ctypes.c_int64(nbytes), nv.stream_ptr(t.device)))
+    return sums
+
+
+def u8bgr_to_rgb(frames_u8, dtype=torch.float32):
+    """uint8 BGR [..., 3] CUDA -> RGB float (x/255)."""
+    if frames_u8.device.type != "cuda" or frames_u8.dtype != torch.uint8 or frames_u8.shape[-1] != 3:
+        raise ValueError("vrgdg_b200: expected a CUDA uint8 tensor [...,3]")
+    s = frames_u8.contiguous()
+    out = torch.empty(s.shape, dtype=dtype, device=s.device)
+    lib = nv.load_library()
+    with torch.cuda.device(s.device):
+        nv.check(lib.vrgdg_u8bgr_to_rgb(nv.ptr(s), nv.ptr(out), s.numel() // 3, nv.DTYPE_CODE[dtype], nv.stream_ptr(s.device)))
+    return out
+
+
+def rgb_to_u8bgr(frames):
+    t = nv.require_cuda(frames, "frames")
+    if t.shape[-1] != 3:
+        raise ValueError("vrgdg_b200: expected [...,3]")
+    out = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_rgb_to_u8bgr(nv.ptr(t), nv.ptr(out), t.numel() // 3, nv.DTYPE_CODE[t.dtype], nv.stream_ptr(t.device)))
+    return out

@@ -1,0 +1,190 @@
+/*
+ * vrgdg_b200.h — C ABI of libvrgdg_b200.so: B200 (sm_100a) kernels for the per-pixel video
+ * post-processing hot path of the comfyui-vrgamedevgirl node pack.
+ *
+ * The reference is pure Python (no FFI of its own); each entry point below replaces the tensor
+ * math of one reference function and is what a ctypes stub in the reference would bind
+ * (see INTEGRATION.md).  Reference citations are file:line into the reference tree.
+ *
+ * Conventions
+ *   - every function returns int: 0 = VRGDG_OK, <0 = VRGDG_E_*; text via vrgdg_last_error()
+ *     (thread-local).  No C++ exceptions cross the boundary, no torch types in signatures.
+ *   - all pointers are DEVICE pointers unless a name ends in _host; the library never allocates
+ *     or frees frame memory (the caller's allocator owns it); `in` and `out` must not alias
+ *     for the stencil / tile entry points.
+ *   - frames are ComfyUI IMAGE layout [B,H,W,C] contiguous, channel fastest, values in [0,1].
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued there, nothing
+ *     synchronises the device.  The current CUDA device must be the one owning the pointers.
+ *   - dtype: element type of frames (and of ext_noise).  Arithmetic is fp32 inside the kernels.
+ */
+#ifndef VRGDG_B200_H
+#define VRGDG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRGDG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VRGDG_API __attribute__((visibility("default")))
+#else
+#define VRGDG_API
+#endif
+
+enum {
+  VRGDG_OK = 0,
+  VRGDG_E_INVALID = -1,      /* bad argument (shape, enum, null pointer)  -> ValueError   */
+  VRGDG_E_UNSUPPORTED = -2,  /* valid but not implemented combination      -> ValueError   */
+  VRGDG_E_CUDA = -3,         /* CUDA runtime / driver error                -> RuntimeError */
+  VRGDG_E_ALIGN = -4         /* pointer not aligned to the element size    -> ValueError   */
+};
+
+enum { VRGDG_F32 = 0, VRGDG_F16 = 1, VRGDG_BF16 = 2 };
+
+/* 3x3 stencil epilogues.  nodes.py:182-209 (box unsharp), :266-289 (laplacian, numpy path),
+ * :249-258 (laplacian, torch path: opposite sign), :357-384 (sobel, numpy), :329-349 (sobel, torch: +1e-6) */
+enum {
+  VRGDG_STENCIL_NONE = 0,
+  VRGDG_STENCIL_BOX_UNSHARP = 1,
+  VRGDG_STENCIL_LAPLACIAN_CPU = 2,
+  VRGDG_STENCIL_LAPLACIAN_GPU = 3,
+  VRGDG_STENCIL_SOBEL_CPU = 4,
+  VRGDG_STENCIL_SOBEL_GPU = 5
+};
+
+/* border of the 3x3 window: numpy paths use np.pad(mode="edge"); torch paths zero-pad. */
+enum { VRGDG_BORDER_REPLICATE = 0, VRGDG_BORDER_ZERO = 1 };
+
+/* how (seed, frame index) key the counter-based RNG.
+ *   PER_CLIP : key = seed, counter carries the absolute frame index frame0+i
+ *              (FastFilmGrain nodes.py:51, _apply_film_grain_tensor VRGDG_LUTVideoTools.py:268-272)
+ *   PER_FRAME: key = (seed + frame0 + i) & 0x7FFFFFFF, frame counter = 0
+ *              (_apply_seeded_grain VRGDG_StandaloneVideoEnhancerNodes.py:266-269)
+ * Both make the result independent of batch boundaries and of how frames are sharded. */
+enum { VRGDG_SEED_PER_CLIP = 0, VRGDG_SEED_PER_FRAME = 1 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+VRGDG_API int vrgdg_version(void);
+VRGDG_API const char* vrgdg_last_error(void);
+/* sm count and compute capability of the current device */
+VRGDG_API int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernel launches this library has enqueued since load (all threads) */
+VRGDG_API int64_t vrgdg_launch_count(void);
+/* name of the code path the last tile call on this thread took: "tma" or "generic" */
+VRGDG_API const char* vrgdg_last_tile_path(void);
+
+/* ---- 3D LUT, trilinear --------------------------------------------------------------------
+ * Replaces VRGDG_LUTS._apply_cube_lut + the strength blend of apply_lut
+ * (VRGDG_IV_Adjustments.py:289-343, :355-359; _apply_lut_tensor VRGDG_LUTVideoTools.py:172-185).
+ * lut: [S,S,S,3] fp32, index order [blue][green][red][rgb] (:272-274).  dmin/dspan_host: 3 floats
+ * each on the HOST, dspan = clamp(dmax-dmin, 1e-6) already evaluated in the image dtype (:295,:351-352).
+ * channels 3 or 4 (alpha copied through, :341-343).  blend in (0,1]: out = in*(1-blend)+lut*blend when
+ * blend<1; one_minus_blend is passed separately because the reference forms (1.0-blend) in double.
+ * Output is bit-identical to the reference CPU path for fp32 frames. */
+VRGDG_API int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype,
+                      const float* lut, int lut_size,
+                      const float* dmin_host, const float* dspan_host,
+                      float blend, float one_minus_blend, void* stream);
+
+/* ---- film grain ------------------------------------------------------------------------------
+ * Replaces FastFilmGrain.apply_grain (nodes.py:49-60), _apply_film_grain_tensor
+ * (VRGDG_LUTVideoTools.py:262-277) and _apply_seeded_grain (VRGDG_StandaloneVideoEnhancerNodes.py:261-275).
+ * z ~ N(0,1) per element from Philox4x32-10 + Box-Muller keyed per seed_mode, or read from ext_noise
+ * ([B,H,W,3], same dtype as frames) when non-null; then
+ *   out = clamp(x + I*(sat*z' + one_minus_sat*z_g), 0, 1),  z' = (2 z_r, z_g, 3 z_b).
+ * With ext_noise and fp32 frames every rounding step equals the reference's (bit-identical). */
+VRGDG_API int vrgdg_grain(const void* in, void* out, int B, int H, int W, int dtype,
+                float intensity, float sat, float one_minus_sat,
+                uint64_t seed, int64_t frame0, int seed_mode,
+                const void* ext_noise, void* stream);
+
+/* ---- 3x3 stencil sharpeners --------------------------------------------------------------------
+ * Replaces FastUnsharpSharpen / FastLaplacianSharpen / FastSobelSharpen (nodes.py:156-384) and
+ * _apply_unsharp (VRGDG_StandaloneVideoEnhancerNodes.py:233-258).  TMA-tiled when rows are 16-byte
+ * aligned, generic tile loader otherwise (same arithmetic). */
+VRGDG_API int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, int dtype,
+                     int op, float strength, int border, void* stream);
+
+/* ---- colour match (Reinhard LAB mean/std transfer) ---------------------------------------------
+ * Replaces ColorMatchToReference.match_color (nodes.py:97-121) incl. kornia rgb_to_lab / lab_to_rgb.
+ * Step 1: per-frame raw LAB sums over image rows [row0,row0+rows): sums[b] = {n, S_L, S_a, S_b, S_LL, S_aa, S_bb}
+ *         (7 doubles per frame; fixed-order two-level reduction, deterministic).  Row ranges exist so the
+ *         reference image can be sharded by rows across ranks and merged by addition.
+ * Step 2: params[b] = {mu_img[3], sd_img[3], mu_ref[3], sd_ref[3]} fp32, sd = unbiased std + 1e-5 (:99-100,:109-110).
+ *         n_ref is 1 (broadcast) or B.
+ * Step 3: out = clamp(lab_to_rgb(t*((lab-mu)/sd*sd_ref+mu_ref) + (1-t)*lab)). */
+VRGDG_API int64_t vrgdg_lab_moments_scratch_bytes(int B);
+VRGDG_API int vrgdg_lab_moments(const void* in, int B, int H, int W, int dtype, int row0, int rows,
+                      double* sums, void* scratch, int64_t scratch_bytes, void* stream);
+VRGDG_API int vrgdg_colormatch_params(const double* frame_sums, int B, const double* ref_sums, int n_ref,
+                            float* params, void* stream);
+VRGDG_API int vrgdg_colormatch_apply(const void* in, void* out, int B, int H, int W, int dtype,
+                           const float* params, float t, float one_minus_t, void* stream);
+
+/* ---- fused chain ---------------------------------------------------------------------------------
+ * One pass over HBM for  grain -> colour match -> 3D LUT -> 3x3 stencil -> post-grain , any subset.
+ * Composition semantics = the reference nodes applied one after another on fp32 tensors (each stage
+ * clamps to [0,1] where its node clamps).  post_grain reproduces _apply_effects_batch
+ * (VRGDG_StandaloneVideoEnhancerNodes.py:278-294: unsharp first, seeded grain second). */
+typedef struct vrgdg_chain_desc {
+  /* stage 1: grain before everything else */
+  int32_t grain_enabled;
+  float grain_intensity, grain_sat, grain_one_minus_sat;
+  uint64_t grain_seed;
+  int64_t grain_frame0;
+  int32_t grain_seed_mode;
+  /* stage 2: colour match with precomputed params [B][12] (device) */
+  int32_t colormatch_enabled;
+  const float* cm_params;
+  float cm_t, cm_one_minus_t;
+  /* stage 3: 3D LUT */
+  int32_t lut_enabled;
+  const float* lut;
+  int32_t lut_size;
+  float lut_dmin[3], lut_dspan[3];
+  float lut_blend, lut_one_minus_blend;
+  /* stage 4: stencil */
+  int32_t stencil_op;   /* VRGDG_STENCIL_* */
+  float stencil_strength;
+  int32_t stencil_border;
+  /* stage 5: grain after the stencil */
+  int32_t post_grain_enabled;
+  float post_intensity, post_sat, post_one_minus_sat;
+  uint64_t post_seed;
+  int64_t post_frame0;
+  int32_t post_seed_mode;
+} vrgdg_chain_desc;
+
+VRGDG_API int vrgdg_chain_apply(const void* in, void* out, int B, int H, int W, int dtype,
+                      const vrgdg_chain_desc* desc, void* stream);
+
+/* vrgdg_chain_apply with the first grain stage reading N(0,1) from ext_noise ([B,H,W,3], frame dtype) instead
+ * of the in-kernel generator: lets the fused chain be compared with the reference composition on the same
+ * noise tensor (nodes.py:51 draws it from torch's generator, which no CUDA kernel can reproduce). */
+VRGDG_API int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int W, int dtype,
+                          const vrgdg_chain_desc* desc, const void* ext_noise, void* stream);
+
+/* LAB sums of grain(x) (stage 1 of desc only) so that colour match can follow grain inside the chain
+ * without materialising the grained frames. */
+VRGDG_API int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype,
+                            const vrgdg_chain_desc* desc, double* sums,
+                            void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- uint8 BGR wire format -------------------------------------------------------------------------
+ * _frames_to_tensor / _tensor_to_frames (VRGDG_LUTVideoTools.py:736-752,
+ * VRGDG_StandaloneVideoEnhancerNodes.py:311-324): u8 BGR -> RGB float /255.0 and
+ * clip(x*255,0,255) truncated to u8 -> BGR. */
+VRGDG_API int vrgdg_u8bgr_to_rgb(const uint8_t* in, void* out, int64_t npix, int dtype, void* stream);
+VRGDG_API int vrgdg_rgb_to_u8bgr(const void* in, uint8_t* out, int64_t npix, int dtype, void* stream);
+
+/* Raw N(0,1) stream of the grain generator ([B,H,W,3] fp32), for distribution tests. */
+VRGDG_API int vrgdg_grain_noise(float* out, int B, int H, int W, uint64_t seed, int64_t frame0,
+                      int seed_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRGDG_B200_H */

@@ -1,0 +1,88 @@
+// hostcheck.cpp — TEST INFRASTRUCTURE.  Compiles the kernels' per-pixel arithmetic header
+// (comfyui-vrgamedevgirl_b200/csrc/vrgdg_math.cuh) for the host with g++ -ffp-contract=off so the CPU test
+// suite can compare it with the oracle without a GPU.  Never loaded by the product.
+#include "../../comfyui-vrgamedevgirl_b200/csrc/vrgdg_math.cuh"
+#include <stdint.h>
+
+using namespace vrgdg;
+
+extern "C" {
+
+void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  U4 c{ctr[0], ctr[1], ctr[2], ctr[3]};
+  U4 r = philox4x32<10>(c, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void hc_normals(uint64_t seed, int64_t frame0, int64_t frame, int mode, uint32_t pix0, int64_t n, float* out) {
+  GrainKey gk = grain_key(seed, frame0, frame, mode);
+  for (int64_t i = 0; i < n; ++i) grain_normals<10>(gk, pix0 + (uint32_t)i, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+void hc_grain(const float* in, const float* noise, float* out, int64_t n, float I, float s, float oms, int exact) {
+  for (int64_t i = 0; i < n; ++i) {
+    float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
+    if (exact) grain_blend_exact(r, g, b, noise[3 * i], noise[3 * i + 1], noise[3 * i + 2], I, s, oms);
+    else grain_blend_fast(r, g, b, noise[3 * i], noise[3 * i + 1], noise[3 * i + 2], I, s, oms);
+    out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
+  }
+}
+
+void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, const float* dmin, const float* dspan,
+              float blend, float omb, int exact) {
+  LutParams P;
+  P.lut = lut; P.S = S; P.smax = (float)(S - 1);
+  for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
+  P.blend = blend; P.one_minus_blend = omb;
+  for (int64_t i = 0; i < n; ++i) {
+    float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
+    float x0 = r, x1 = g, x2 = b;
+    if (exact) lut3d_eval<true>(P, r, g, b); else lut3d_eval<false>(P, r, g, b);
+    if (blend < 1.0f) {
+      if (exact) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }
+      else { r = lut_blend<false>(x0, r, blend, omb); g = lut_blend<false>(x1, g, blend, omb); b = lut_blend<false>(x2, b, blend, omb); }
+    }
+    out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
+  }
+}
+
+void hc_rgb_to_lab(const float* in, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) rgb_to_lab(in[3 * i], in[3 * i + 1], in[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+void hc_lab_to_rgb(const float* in, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) lab_to_rgb(in[3 * i], in[3 * i + 1], in[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+}
+
+void hc_colormatch(const float* in, float* out, int64_t n, const float* params, float t, float omt) {
+  for (int64_t i = 0; i < n; ++i) {
+    float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
+    colormatch_pixel(r, g, b, params, t, omt);
+    out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
+  }
+}
+
+// frames [H][W][3], border 0 replicate / 1 zero
+void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int border) {
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x)
+      for (int c = 0; c < 3; ++c) {
+        float n9[9];
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            float v;
+            if (border == 0) {
+              yy = yy < 0 ? 0 : (yy >= H ? H - 1 : yy);
+              xx = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);
+              v = in[(yy * W + xx) * 3 + c];
+            } else {
+              v = (yy < 0 || yy >= H || xx < 0 || xx >= W) ? 0.0f : in[(yy * W + xx) * 3 + c];
+            }
+            n9[(dy + 1) * 3 + dx + 1] = v;
+          }
+        out[(y * W + x) * 3 + c] = stencil_epilogue(op, n9, s);
+      }
+}
+
+}  // extern "C"
