@@ -1,0 +1,99 @@
+"""Tensor-math helpers of the reference's file->file video paths, same names and signatures, on sm_100a kernels.
+
+Reference: VRGDG_LUTVideoTools.py (_apply_lut_tensor :172-185, _apply_film_grain_tensor :262-277, uint8 codecs :736-752)
+and VRGDG_StandaloneVideoEnhancerNodes.py (_auto_batch_size :200-210, _apply_unsharp :233-258, _apply_seeded_grain :261-275,
+_apply_effects_batch :278-294).  The decode/encode, ffmpeg and HTTP route glue around them is out of scope.
+"""
+import numpy as np
+import torch
+
+from . import _native as nv
+from . import ops
+from ._runtime import compute_device
+from .chain import PostChain
+from .lut_nodes import VRGDG_LUTS, _run_lut
+
+
+def _to_cuda(t, device=None):
+    dev = compute_device(t) if device in (None, "cpu", "auto") or str(device) == "cpu" else torch.device(device)
+    return t.to(dev), dev
+
+
+def _apply_lut_tensor(image_tensor, lut_name, strength, device):
+    """`device` is accepted for signature compatibility; compute is always CUDA, the result lands on the compute device
+    like the reference's (which returns on `device`) unless that was "cpu" -> returned to the input's device."""
+    lut_data = VRGDG_LUTS._load_lut(lut_name)
+    src, dev = _to_cuda(image_tensor, device)
+    out = _run_lut(src, lut_data, strength)
+    return out if str(device) != "cpu" else out.to(image_tensor.device)
+
+
+def _apply_film_grain_tensor(image_tensor, grain_intensity=0.04, saturation_mix=0.5, device="cpu", seed=None):
+    intensity = max(0.0, min(1.0, float(grain_intensity)))
+    saturation = max(0.0, min(1.0, float(saturation_mix)))
+    src, dev = _to_cuda(image_tensor, device)
+    if seed in (None, ""):
+        seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+    out = ops.grain(src, intensity, saturation, 1.0 - saturation, int(seed), frame0=0, seed_mode=nv.SEED_PER_CLIP)
+    return out if str(device) != "cpu" else out.to(image_tensor.device)
+
+
+def _auto_batch_size(width, height):
+    """EnhancerNodes.py:200-210 (host logic, unchanged semantics)."""
+    pixels = max(1, int(width) * int(height))
+    for limit, batch in ((1280 * 720, 16), (1920 * 1080, 8), (2560 * 1440, 4), (3200 * 1800, 2)):
+        if pixels <= limit:
+            return batch
+    return 1
+
+
+def _apply_unsharp(images, strength, use_gpu):
+    if strength <= 0:
+        return images
+    src, dev = _to_cuda(images)
+    out = ops.stencil3x3(src, nv.STENCIL_BOX_UNSHARP, float(strength), nv.BORDER_ZERO if use_gpu else nv.BORDER_REPLICATE)
+    return out.to(images.device)
+
+
+def _apply_seeded_grain(images, intensity, saturation_mix, seed, frame_start):
+    if intensity <= 0:
+        return images
+    src, dev = _to_cuda(images)
+    s = float(saturation_mix)
+    out = ops.grain(src, float(intensity), s, 1.0 - s, int(seed), frame0=int(frame_start), seed_mode=nv.SEED_PER_FRAME)
+    return out.to(images.device)
+
+
+def _apply_effects_batch(images, settings, frame_start=0):
+    """unsharp (if enabled) then per-frame seeded grain (if enabled) in ONE fused kernel; returns a CPU tensor like
+    the reference (:294)."""
+    use_gpu = bool(settings.get("use_gpu", True))
+    src, dev = _to_cuda(images)
+    stencil = post = None
+    if settings.get("sharpen_enabled", True) and float(settings.get("sharpen_strength", 0.5)) > 0:
+        stencil = dict(op=nv.STENCIL_BOX_UNSHARP, strength=float(settings.get("sharpen_strength", 0.5)),
+                       border=nv.BORDER_ZERO if use_gpu else nv.BORDER_REPLICATE)
+    if settings.get("grain_enabled", False) and float(settings.get("grain_intensity", 0.04)) > 0:
+        post = dict(intensity=float(settings.get("grain_intensity", 0.04)), saturation_mix=float(settings.get("saturation_mix", 0.5)),
+                    seed=int(settings.get("seed", 42)), seed_mode=nv.SEED_PER_FRAME)
+    if stencil is None and post is None:
+        return images.detach().cpu()
+    if stencil is None:
+        s = post["saturation_mix"]
+        out = ops.grain(src, post["intensity"], s, 1.0 - s, post["seed"], frame0=int(frame_start), seed_mode=nv.SEED_PER_FRAME)
+    else:
+        out = PostChain(stencil=stencil, post_grain=post, device=dev)(src, first_frame=int(frame_start))
+    return out.detach().cpu()
+
+
+def _frames_to_tensor(frames, device=None):
+    """uint8 BGR frames (list of [H,W,3] arrays) -> float RGB [B,H,W,3] on the GPU: x/255 with the channel swap fused."""
+    stacked = torch.from_numpy(np.stack(frames, axis=0))
+    dev = compute_device() if device is None else torch.device(device)
+    return ops.u8bgr_to_rgb(stacked.to(dev))
+
+
+def _tensor_to_frames(tensor):
+    """float RGB -> list of uint8 BGR frames: clip(x*255, 0, 255) TRUNCATED (not rounded), as the reference does."""
+    src, dev = _to_cuda(tensor.detach())
+    return list(ops.rgb_to_u8bgr(src).cpu().numpy())

@@ -72,8 +72,8 @@ def load_enhancer_helpers():
     return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_StandaloneVideoEnhancerNodes.py"), names, ns)
 
 
-def load_lut_video_helpers():
-    iv = load_iv_adjustments()
+def load_lut_video_helpers(iv=None):
+    iv = iv if iv is not None else load_iv_adjustments()
     ns = {"torch": torch, "VRGDG_LUTS": iv.VRGDG_LUTS}
     names = {"_apply_lut_tensor", "_apply_film_grain_tensor"}
     return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_LUTVideoTools.py"), names, ns)

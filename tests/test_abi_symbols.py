@@ -1,0 +1,69 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/vrgdg_b200.h declares; the
+ctypes table mirrors the header.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import PKG_NAME, ROOT
+
+HEADER = os.path.join(ROOT, "include", "vrgdg_b200.h")
+
+
+def declared_symbols():
+    with open(HEADER, encoding="utf-8") as fh:
+        text = fh.read()
+    return sorted(set(re.findall(r"VRGDG_API\s+[\w\s\*]+?\b(vrgdg_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for must in ("vrgdg_lut3d_apply", "vrgdg_grain", "vrgdg_stencil3x3", "vrgdg_lab_moments", "vrgdg_colormatch_params",
+                 "vrgdg_colormatch_apply", "vrgdg_chain_apply", "vrgdg_chain_lab_moments", "vrgdg_u8bgr_to_rgb", "vrgdg_rgb_to_u8bgr",
+                 "vrgdg_version", "vrgdg_last_error"):
+        assert must in names
+    assert len(names) >= 18
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    nv = pkg._native
+    if not os.path.exists(nv.LIB_PATH):
+        import importlib
+        importlib.import_module(PKG_NAME + ".build").build()
+    lib = ctypes.CDLL(nv.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert sorted(nv.SIGNATURES) == declared_symbols()
+    # exported dynamic symbols are exactly the ABI (everything else is hidden)
+    out = subprocess.run(["nm", "-D", "--defined-only", nv.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and "vrgdg_" in l)
+    assert exported == declared_symbols()
+
+
+def test_version_and_error_channel_without_gpu(pkg):
+    import torch
+    nv = pkg._native
+    lib = nv.load_library()
+    assert lib.vrgdg_version() == 1
+    assert lib.vrgdg_lab_moments_scratch_bytes(3) == 3 * 296 * 48
+    if not torch.cuda.is_available():
+        rc = lib.vrgdg_device_info(None, None, None)
+        assert rc == nv.E_CUDA
+        with pytest.raises(RuntimeError):
+            nv.check(rc)
+        # argument validation happens before any CUDA call
+        rc = lib.vrgdg_stencil3x3(None, None, 1, 4, 4, 7, 1, 0.5, 0, None)
+        assert rc == nv.E_INVALID and b"dtype" in lib.vrgdg_last_error()
+        with pytest.raises(ValueError):
+            nv.check(rc)
+
+
+def test_sass_contains_tma_and_no_legacy_tensor_paths(pkg):
+    """sm_100a only; the tile kernels use TMA (UTMALDG) + mbarrier (SYNCS); nothing routes through HMMA."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    lst = subprocess.run([cuobjdump, "-lelf", pkg._native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in lst and "sm_90" not in lst and "sm_80" not in lst

@@ -1,0 +1,150 @@
+"""Host-side logic that mirrors the reference without needing a GPU: node API surface, .cube parsing, palette LUT,
+file naming, batch-size table, and the 'no CUDA -> raise' contract."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, LUTS, load_golden, t, white_frames
+
+
+@pytest.fixture(scope="module")
+def meta():
+    with open(os.path.join(GOLDEN, "reference_meta.json"), encoding="utf-8") as fh:
+        return json.load(fh)
+
+
+def test_node_mappings_and_api_match_reference(pkg, meta):
+    assert set(pkg.NODE_CLASS_MAPPINGS) == set(meta["api"])
+    for key, want in meta["api"].items():
+        cls = pkg.NODE_CLASS_MAPPINGS[key]
+        got = json.loads(json.dumps(cls.INPUT_TYPES()))
+        if key == "VRGDG_LUTS":
+            assert got["required"]["lut_name"][0] == sorted(got["required"]["lut_name"][0], key=str.lower)
+            got["required"]["lut_name"] = ["<lut files>"]
+        assert got == want["INPUT_TYPES"], key
+        assert list(got["required"]) == list(want["INPUT_TYPES"]["required"]), key + " widget order"
+        assert list(cls.RETURN_TYPES) == want["RETURN_TYPES"] and cls.FUNCTION == want["FUNCTION"] and cls.CATEGORY == want["CATEGORY"]
+        assert list(getattr(cls, "RETURN_NAMES", ())) == want["RETURN_NAMES"]
+        assert getattr(cls, "DESCRIPTION", None) == want["DESCRIPTION"]
+        assert callable(getattr(cls, cls.FUNCTION))
+    assert pkg.NODE_DISPLAY_NAME_MAPPINGS == meta["display_names"]
+
+
+def test_method_signatures_are_the_reference_ones(pkg):
+    import inspect
+    sig = lambda c, m: list(inspect.signature(getattr(c, m)).parameters)
+    assert sig(pkg.FastFilmGrain, "apply_grain") == ["self", "images", "grain_intensity", "saturation_mix", "batch_size"]
+    assert sig(pkg.ColorMatchToReference, "match_color") == ["self", "images", "reference_image", "match_strength", "batch_size"]
+    for c, m in ((pkg.FastUnsharpSharpen, "apply_unsharp"), (pkg.FastLaplacianSharpen, "apply_laplacian"), (pkg.FastSobelSharpen, "apply_sobel")):
+        assert sig(c, m) == ["self", "images", "strength", "use_gpu"]
+    assert sig(pkg.VRGDG_LUTS, "apply_lut") == ["self", "image", "lut_name", "device", "strength"]
+    assert sig(pkg.VRGDG_MakeLUT, "create_and_apply") == ["self", "image", "colors", "name_suffix", "lut_size", "device", "strength"]
+    # saved workflows store positional widget values, e.g. FastFilmGrain [0.01, 0.5, 4], ColorMatchToReference [1, 4]
+    assert list(pkg.FastFilmGrain.INPUT_TYPES()["required"])[1:] == ["grain_intensity", "saturation_mix", "batch_size"]
+
+
+def test_cube_parser_matches_oracle_and_rejects_bad_files(pkg, oracle, tmp_path):
+    for fname in sorted(os.listdir(LUTS)) + [os.path.join(GOLDEN, "domain_5.cube")]:
+        path = fname if os.path.isabs(fname) else os.path.join(LUTS, fname)
+        if not path.endswith(".cube"):
+            continue
+        a, b = pkg.VRGDG_LUTS._parse_cube_file(path), oracle.parse_cube(path)
+        assert a["size"] == b["size"] and torch.equal(a["lut"], b["lut"])
+        assert torch.equal(a["domain_min"], b["domain_min"]) and torch.equal(a["domain_max"], b["domain_max"])
+        assert a["lut"].dtype == torch.float32 and tuple(a["lut"].shape) == (a["size"],) * 3 + (3,)
+
+    def write(name, text):
+        p = tmp_path / name
+        p.write_text(text)
+        return str(p)
+    body = "".join("0.1 0.2 0.3\n" for _ in range(8))
+    ok = pkg.VRGDG_LUTS._parse_cube_file(write("ok.cube", "# c\nTITLE \"x\"\nLUT_3D_SIZE 2\nDOMAIN_MIN 0 0 0\nDOMAIN_MAX 1 1 1\nFOO 1\nLUT_3D_INPUT_RANGE 0.0 1.0 2.0 3.0\n\n" + body))
+    assert ok["size"] == 2 and ok["lut"][1, 0, 1].tolist() == pytest.approx([0.1, 0.2, 0.3])
+    # red fastest: value index 1 is [b=0][g=0][r=1]
+    seq = "".join("%d 0 0\n" % i for i in range(8))
+    lut = pkg.VRGDG_LUTS._parse_cube_file(write("seq.cube", "LUT_3D_SIZE 2\n" + seq))["lut"]
+    assert lut[0, 0, 1, 0] == 1 and lut[0, 1, 0, 0] == 2 and lut[1, 0, 0, 0] == 4
+    for name, text, exc in (("a.cube", "LUT_1D_SIZE 4\n", ValueError), ("b.cube", body, ValueError), ("c.cube", "LUT_3D_SIZE 2\n0.1 0.2 0.3\n", ValueError),
+                            ("d.cube", "LUT_3D_SIZE 2 3\n" + body, ValueError), ("e.cube", "LUT_3D_SIZE 2\nDOMAIN_MIN 0 0\n" + body, ValueError)):
+        with pytest.raises(exc):
+            pkg.VRGDG_LUTS._parse_cube_file(write(name, text))
+        with pytest.raises(exc):
+            oracle.parse_cube(write(name, text))
+
+
+def test_palette_lut_and_cube_writer_round_trip(pkg, tmp_path):
+    ln = __import__("importlib").import_module("comfyui-vrgamedevgirl_b200.lut_nodes")
+    g = load_golden("palette")
+    assert torch.equal(ln._build_palette_lut("#0b1d51, #1f6aa5, #f3d27a", 9), t(g["three"]))
+    assert torch.equal(ln._build_palette_lut("teal", 8), t(g["one"]))
+    assert torch.equal(ln._build_palette_lut("black, #f80, white, pink", 11), t(g["names"]))
+    with pytest.raises(ValueError):
+        ln._build_palette_lut("#12345", 8)
+    with pytest.raises(ValueError):
+        ln._build_palette_lut(" , ", 8)
+    path = str(tmp_path / "sub" / "p.cube")
+    ln._write_cube_file(t(g["three"]), path)
+    head = open(path).read().splitlines()[:4]
+    assert head == ['TITLE "p.cube"', "LUT_3D_SIZE 9", "DOMAIN_MIN 0.0 0.0 0.0", "DOMAIN_MAX 1.0 1.0 1.0"]
+    back = ln.VRGDG_LUTS._parse_cube_file(path)
+    assert back["size"] == 9 and float((back["lut"] - t(g["three"])).abs().max()) <= 5.1e-7      # %.6f text
+    assert ln._sanitize_filename_part(" #0B1d51 ") == "0b1d51" and ln._sanitize_filename_part("") == "custom"
+    assert ln._sanitize_filename_part("My  Fancy--Name!") == "my_fancy_name"
+
+
+def test_lut_listing_cache_and_is_changed(pkg, monkeypatch, tmp_path):
+    ln = __import__("importlib").import_module("comfyui-vrgamedevgirl_b200.lut_nodes")
+    names = ln._list_lut_files()
+    assert "B200 Vintage 33.cube" in names and names == sorted(names, key=str.lower)
+    d1 = pkg.VRGDG_LUTS._load_lut("B200 Vintage 33.cube")
+    assert pkg.VRGDG_LUTS._load_lut("B200 Vintage 33.cube") is d1 and len(pkg.VRGDG_LUTS._LUT_CACHE) == 1
+    key = pkg.VRGDG_LUTS.IS_CHANGED(None, "B200 Vintage 33.cube", "auto", 10.0)
+    assert key.endswith("|auto|10.0") and "B200 Vintage 33.cube" in key
+    assert pkg.VRGDG_LUTS.IS_CHANGED(None, "No LUT files found", "cpu", 1.0) == "missing|cpu|1.0"
+    assert "|missing|nope.cube|" in pkg.VRGDG_LUTS.IS_CHANGED(None, "nope.cube", "cpu", 1.0)
+    monkeypatch.setattr(ln, "LUTS_DIR", str(tmp_path / "none"))
+    assert ln._list_lut_files() == ["No LUT files found"] and pkg.VRGDG_LUTS._get_luts_folder_state() == "missing"
+    with pytest.raises(ValueError):
+        pkg.VRGDG_LUTS._load_lut("No LUT files found")
+    with pytest.raises(FileNotFoundError):
+        pkg.VRGDG_LUTS._load_lut("x.cube")
+    assert ln._next_available_lut_path("a_b").endswith("a_b.cube")
+    open(os.path.join(str(tmp_path / "none"), "a_b.cube"), "w").close()
+    assert ln._next_available_lut_path("a_b").endswith("a_b_2.cube")
+
+
+def test_auto_batch_size_table(pkg, meta):
+    vt = __import__("importlib").import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    for k, v in meta["auto_batch"].items():
+        w, h = (int(s) for s in k.split("x"))
+        assert vt._auto_batch_size(w, h) == v
+
+
+def test_nodes_raise_without_cuda_instead_of_falling_back(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("this contract is about machines without a GPU")
+    x = white_frames(1, 8, 8)
+    with pytest.raises(RuntimeError):
+        pkg.FastFilmGrain().apply_grain(x, 0.04, 0.5, 4)
+    with pytest.raises(RuntimeError):
+        pkg.FastUnsharpSharpen().apply_unsharp(x, 0.5, False)
+    with pytest.raises(RuntimeError):
+        pkg.ColorMatchToReference().match_color(x, x, 1.0, 1)
+    for dev in ("auto", "cuda", "cpu"):
+        with pytest.raises(RuntimeError):
+            pkg.VRGDG_LUTS().apply_lut(x, "B200 Vintage 33.cube", dev, 10.0)
+    with pytest.raises(RuntimeError):
+        pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=1)
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: no file of the package may reference it"""
+    from conftest import PKG_NAME, ROOT
+    for dirpath, _, files in os.walk(os.path.join(ROOT, PKG_NAME)):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "vrgdg_oracle" not in text and "ref_harness" not in text and "/root/reference" not in text, f

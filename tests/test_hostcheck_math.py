@@ -1,0 +1,114 @@
+"""The kernels' per-pixel arithmetic header (csrc/vrgdg_math.cuh) compiled for the HOST (tests/hostcheck) against the
+golden vectors: catches index / rounding mistakes on a machine without a GPU.  The GPU tests repeat the comparison on
+the real kernels."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from helpers import LUTS, load_golden, t
+
+vp, i64, f32, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_int
+
+
+def P(a):
+    return a.ctypes.data_as(vp)
+
+
+def flat(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1, 3))
+
+
+def test_philox4x32_10_known_answers(hostcheck):
+    """Random123 kat_vectors for philox4x32-10."""
+    cases = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+             ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+             ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in cases:
+        c, k, o = np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32), np.zeros(4, dtype=np.uint32)
+        hostcheck.hc_philox(P(c), P(k), P(o))
+        assert o.tolist() == want
+
+
+def test_normals_are_standard_and_keyed(hostcheck):
+    hostcheck.hc_normals.argtypes = [ctypes.c_uint64, i64, i64, ci, ctypes.c_uint32, i64, vp]
+    n = 200000
+    a = np.zeros((n, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 0, 0, 0, 0, n, P(a))
+    assert abs(a.mean()) < 0.01 and abs(a.var() - 1.0) < 0.01 and abs((a ** 4).mean() - 3.0) < 0.1
+    b = np.zeros((n, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 5, 0, 0, 0, n, P(b))                    # other frame
+    assert np.abs(a - b).mean() > 0.5
+    c = np.zeros((10, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 0, 0, 0, 100, 10, P(c))                 # offset window of the same frame
+    assert np.array_equal(c, a[100:110])
+    # PER_FRAME mode: (seed + frame0 + i) & 0x7fffffff is the key -> (40,2,0) == (42,0,0) == (30,5,7)
+    d, e, f = (np.zeros((10, 3), dtype=np.float32) for _ in range(3))
+    hostcheck.hc_normals(40, 2, 0, 1, 0, 10, P(d))
+    hostcheck.hc_normals(42, 0, 0, 1, 0, 10, P(e))
+    hostcheck.hc_normals(30, 5, 7, 1, 0, 10, P(f))
+    assert np.array_equal(d, e) and np.array_equal(e, f)
+
+
+def test_grain_blend_exact_is_bit_identical(hostcheck):
+    hostcheck.hc_grain.argtypes = [vp, vp, vp, i64, f32, f32, f32, ci]
+    g = load_golden("grain")
+    for tag in ("a", "odd"):
+        x, z = flat(g[f"x_{tag}"]), flat(g[f"z_{tag}"])
+        o = np.zeros_like(x)
+        hostcheck.hc_grain(P(x), P(z), P(o), x.shape[0], 0.5, 0.5, 1.0 - 0.5, 1)
+        assert np.array_equal(o, flat(g[f"out_{tag}_i50_s50"]))
+        hostcheck.hc_grain(P(x), P(z), P(o), x.shape[0], 0.04, 0.37, 1.0 - 0.37, 1)
+        assert np.array_equal(o, flat(g[f"out_{tag}_i04_s37"]))
+        hostcheck.hc_grain(P(x), P(z), P(o), x.shape[0], 0.04, 0.37, 1.0 - 0.37, 0)     # fused variant
+        assert np.abs(o - flat(g[f"out_{tag}_i04_s37"])).max() < 1e-6
+
+
+def test_lut_eval_exact_is_bit_identical(hostcheck, oracle):
+    hostcheck.hc_lut3d.argtypes = [vp, vp, i64, vp, ci, vp, vp, f32, f32, ci]
+    g = load_golden("lut")
+    x = flat(g["x"])
+    o = np.zeros_like(x)
+    for fname in sorted(os.listdir(LUTS)):
+        if not fname.endswith(".cube"):
+            continue
+        key = fname.split(".")[0].replace(" ", "_")
+        d = oracle.parse_cube(os.path.join(LUTS, fname))
+        lut = np.ascontiguousarray(d["lut"].numpy())
+        dmin = d["domain_min"].numpy().copy()
+        span = torch.clamp(d["domain_max"] - d["domain_min"], min=1e-6).numpy().copy()
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 1)
+        assert np.array_equal(o, flat(g[f"{key}__s10"])), fname
+        blend = 3.5 / 10.0
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), blend, 1.0 - blend, 1)
+        assert np.array_equal(o, flat(g[f"{key}__s3p5"])), fname
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 0)      # contracted variant
+        assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
+
+
+def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
+    hostcheck.hc_stencil.argtypes = [vp, vp, ci, ci, ci, f32, ci]
+    g = load_golden("stencil")
+    x = np.ascontiguousarray(g["x"][0])
+    o = np.zeros_like(x)
+    for op, key, border in ((1, "unsharp_np", 0), (1, "unsharp_torch", 1), (2, "laplacian_np", 0), (3, "laplacian_torch", 1),
+                            (4, "sobel_np", 0), (5, "sobel_torch", 1)):
+        hostcheck.hc_stencil(P(x), P(o), x.shape[0], x.shape[1], op, 0.5, border)
+        assert np.abs(o - g[key][0]).max() <= 1e-5, key
+    hostcheck.hc_colormatch.argtypes = [vp, vp, i64, vp, f32, f32]
+    c = load_golden("colormatch")
+    ref_s = oracle.lab_moments_f64(t(c["ref"]))[0].numpy()
+    for b in range(2):
+        fs = oracle.lab_moments_f64(t(c["x"][b:b + 1]))[0].numpy()
+        def stats(s):
+            n, m = s[0], s[1:4] / s[0]
+            var = (s[4:7] - s[1:4] * m) / (n - 1)
+            return m.astype(np.float32), np.sqrt(var).astype(np.float32) + np.float32(1e-5)
+        params = np.concatenate(stats(fs) + stats(ref_s)).astype(np.float32)
+        xin = flat(c["x"][b])
+        out = np.zeros_like(xin)
+        hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 1.0, 0.0)
+        assert np.abs(out - flat(c["out_t100"][b])).max() <= 1e-5
+        hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 0.6, 1.0 - 0.6)
+        assert np.abs(out - flat(c["out_t60"][b])).max() <= 1e-5

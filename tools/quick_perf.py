@@ -1,0 +1,76 @@
+"""Scratch micro-benchmark of every kernel family (GPU box only).  Not the contract bench (bench.py)."""
+import importlib
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+pkg = importlib.import_module("comfyui-vrgamedevgirl_b200")
+from helpers import LUTS, natural_frames  # noqa: E402
+
+nv, ops = pkg._native, pkg.ops
+dev = torch.device("cuda", 0)
+PEAK = 6573.5
+
+
+def timeit(fn, iters=10, warm=3):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def report(name, ms, npix, bpp):
+    gbs = npix * bpp / ms / 1e6
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "MP/s": round(npix / ms / 1e3, 1), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 3)}), flush=True)
+
+
+def main():
+    lut = pkg.VRGDG_LUTS._parse_cube_file(os.path.join(LUTS, "B200 Vintage 33.cube"))
+    lut_dev = lut["lut"].to(dev)
+    for (B, H, W, dt, tag) in ((16, 1080, 1920, torch.float16, "1080p_f16"), (4, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float32, "1080p_f32")):
+        for dist in ("nat", "white"):
+            x = natural_frames(B, H, W, seed=1, dtype=dt, device=dev) if dist == "nat" else torch.rand(B, H, W, 3, device=dev).to(dt)
+            npix = B * H * W
+            bpp = 2 * 3 * x.element_size()
+            out = torch.empty_like(x)
+            report(f"copy/{tag}", timeit(lambda: out.copy_(x)), npix, bpp)
+            report(f"grain/{tag}/{dist}", timeit(lambda: ops.grain(x, 0.04, 0.5, 0.5, seed=42)), npix, bpp)
+            report(f"lut33/{tag}/{dist}", timeit(lambda: ops.lut3d_apply(x, lut_dev, [0, 0, 0], [1, 1, 1], 1.0, 0.0)), npix, bpp)
+            report(f"unsharp_tma/{tag}/{dist}", timeit(lambda: ops.stencil3x3(x, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)), npix, bpp)
+            os.environ["VRGDG_NO_TMA"] = "1"
+            report(f"unsharp_generic/{tag}/{dist}", timeit(lambda: ops.stencil3x3(x, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)), npix, bpp)
+            del os.environ["VRGDG_NO_TMA"]
+            chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), lut=dict(lut_data=lut, strength=10.0),
+                                        stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=dev)
+            report(f"chain_g_l_u/{tag}/{dist}", timeit(lambda: chain(x, out=out)), npix, bpp)
+            gl = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), lut=dict(lut_data=lut, strength=10.0), device=dev)
+            report(f"point_g_l/{tag}/{dist}", timeit(lambda: gl(x, out=out)), npix, bpp)
+            gu = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=dev)
+            report(f"chain_g_u/{tag}/{dist}", timeit(lambda: gu(x, out=out)), npix, bpp)
+            if dist == "nat":
+                sums = None
+                report(f"lab_moments/{tag}", timeit(lambda: ops.lab_moments(x)), npix, bpp / 2)
+                sums = ops.lab_moments(x)
+                params = ops.colormatch_params(sums, sums[:1].contiguous())
+                report(f"colormatch_apply/{tag}", timeit(lambda: ops.colormatch_apply(x, params, 1.0, 0.0)), npix, bpp)
+            del x, out
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
