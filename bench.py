@@ -55,7 +55,7 @@ def recorded_traffic():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons sampled every 50 ms during the timed region (NVML)."""
+    """SM clock + throttle reasons sampled every 10 ms during the timed region (NVML)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def result(self):
         s = sorted(self.samples)
@@ -220,13 +220,13 @@ def run_b200(args):
     host_in = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
     host_in.copy_(x)
     e2e_steps = max(1, min(args.steps, 5))
-    res = chain.run_host(host_in, chunk_frames=8, first_frame=first)      # warm-up (also pins the result allocator path)
-    del res
+    host_out = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)      # pinned once, reused every step
+    chain.run_host(host_in, chunk_frames=8, first_frame=first, out=host_out)      # warm-up
     barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for _ in range(e2e_steps):
-        res = chain.run_host(host_in, chunk_frames=8, first_frame=first)
+        res = chain.run_host(host_in, chunk_frames=8, first_frame=first, out=host_out)
         checksum += float(res[0, 0, 0, 0])          # device->host result is read on the host
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps

@@ -34,12 +34,13 @@ def result_device(images, numpy_path=False):
     return images.device
 
 
-def stream_frames(src, fn, chunk, out_device, device=None):
+def stream_frames(src, fn, chunk, out_device, device=None, out=None):
     """Apply fn(cuda_frames, first_frame_index) -> cuda_frames over src [B,...] in chunks of `chunk` frames.
 
     CUDA input: a single call (chunk ignored).  CPU input: chunks are uploaded on a side stream while the previous
     chunk computes, results are downloaded on a third stream; pinned source/result tensors make those copies truly
-    asynchronous (result is pinned when the source is)."""
+    asynchronous (result is pinned when the source is).  `out`: optional preallocated host result (reused across calls so
+    that pinning cost is paid once)."""
     B = int(src.shape[0])
     out_device = torch.device(out_device)
     if src.device.type == "cuda":
@@ -54,7 +55,10 @@ def stream_frames(src, fn, chunk, out_device, device=None):
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream(dev)
         up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        out = torch.empty(src.shape, dtype=src.dtype, pin_memory=src.is_pinned()) if to_cpu else torch.empty(src.shape, dtype=src.dtype, device=out_device)
+        if out is None:
+            out = torch.empty(src.shape, dtype=src.dtype, pin_memory=src.is_pinned()) if to_cpu else torch.empty(src.shape, dtype=src.dtype, device=out_device)
+        elif out.shape != src.shape or out.dtype != src.dtype or out.device != out_device:
+            raise ValueError("vrgdg_b200: `out` must match the source frames in shape and dtype and live on %s" % out_device)
         pending = None
         for i in range(0, B, chunk):
             with torch.cuda.stream(up):

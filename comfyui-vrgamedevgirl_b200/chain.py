@@ -90,6 +90,7 @@ class PostChain:
         d = self._desc(frames, first_frame, keep)
         return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out)
 
-    def run_host(self, frames_cpu, chunk_frames=8, first_frame=0):
-        """Host frames in, host frames out: chunked upload / compute / download on three streams."""
-        return stream_frames(frames_cpu, lambda f, i: self(f, first_frame + i), chunk_frames, torch.device("cpu"), self.device)
+    def run_host(self, frames_cpu, chunk_frames=8, first_frame=0, out=None):
+        """Host frames in, host frames out: chunked upload / compute / download on three streams.  Pass pinned tensors
+        (and a reusable pinned `out`) for asynchronous copies."""
+        return stream_frames(frames_cpu, lambda f, i: self(f, first_frame + i), chunk_frames, torch.device("cpu"), self.device, out=out)

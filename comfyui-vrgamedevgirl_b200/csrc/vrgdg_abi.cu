@@ -107,6 +107,7 @@ void fill_lut(LutParams& L, const float* lut, int S, const float* dmin, const fl
   L.lut = lut; L.S = S; L.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { L.dmin[i] = dmin[i]; L.dspan[i] = dspan[i]; }
   L.blend = blend; L.one_minus_blend = omb;
+  L.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f) ? 1 : 0;
 }
 
 void zero_point(PointParams& P, int B, int H, int W) {
@@ -213,6 +214,7 @@ int vrgdg_grain(const void* in, void* out, int B, int H, int W, int dtype, float
   zero_point(P, B, H, W);
   P.gI = intensity; P.gs = sat; P.goms = one_minus_sat;
   P.seed = seed; P.frame0 = frame0; P.seed_mode = seed_mode; P.ext_noise = ext_noise;
+  grain_make_key(seed, seed_mode, P.gkey);
   const bool exact = ext_noise != nullptr;
 #define PT(T) launch_point<T>(in, out, P, ST_GRAIN, exact, ctx)
   cudaError_t e = DISPATCH_DTYPE(dtype, PT);
@@ -230,7 +232,10 @@ int vrgdg_grain_noise(float* out, int B, int H, int W, uint64_t seed, int64_t fr
   if (rc) return rc;
   int64_t total = (int64_t)B * H * W;
   int grid = (int)(((total + 255) / 256) < (int64_t)ctx.sms * 16 ? ((total + 255) / 256) : (int64_t)ctx.sms * 16);
-  k_grain_noise<<<grid, 256, 0, ctx.stream>>>(out, B, (int64_t)H * W, seed, frame0, seed_mode);
+  if (seed_mode != VRGDG_SEED_PER_CLIP && seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "vrgdg_grain_noise: bad seed_mode %d", seed_mode);
+  GrainKey K;
+  grain_make_key(seed, seed_mode, K);
+  k_grain_noise<<<grid, 256, 0, ctx.stream>>>(out, B, W, (int64_t)H * W, seed, frame0, seed_mode, K);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_grain_noise");
@@ -324,6 +329,7 @@ static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, Po
     mask |= ST_GRAIN;
     P.gI = d->grain_intensity; P.gs = d->grain_sat; P.goms = d->grain_one_minus_sat;
     P.seed = d->grain_seed; P.frame0 = d->grain_frame0; P.seed_mode = d->grain_seed_mode;
+    grain_make_key(P.seed, P.seed_mode, P.gkey);
     P.ext_noise = ext_noise;
   }
   if (d->colormatch_enabled) {
@@ -380,6 +386,7 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
   Q.post_enabled = d->post_grain_enabled ? 1 : 0;
   Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
   Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;
+  grain_make_key(Q.pseed, Q.pseed_mode, Q.pkey);
   return run_tile(in, out, B, H, W, dtype, Q, mask, exact, ctx);
 }
 
@@ -403,6 +410,7 @@ int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, cons
   if (desc->grain_enabled) {
     P.gI = desc->grain_intensity; P.gs = desc->grain_sat; P.goms = desc->grain_one_minus_sat;
     P.seed = desc->grain_seed; P.frame0 = desc->grain_frame0; P.seed_mode = desc->grain_seed_mode;
+    grain_make_key(P.seed, P.seed_mode, P.gkey);
   }
   return moments_common(in, B, H, W, dtype, 0, H, desc->grain_enabled ? &P : nullptr, sums, scratch, scratch_bytes, stream,
                         "vrgdg_chain_lab_moments");

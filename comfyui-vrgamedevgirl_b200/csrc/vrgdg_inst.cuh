@@ -35,7 +35,7 @@ static cudaError_t launch_point_k(const void* in, void* out, const PointParams& 
 template <typename T, int MASK, bool EXACT>
 static cudaError_t launch_point_v(const void* in, void* out, const PointParams& P, const LaunchCtx& ctx) {
   constexpr int PX = (int)(48 / (3 * sizeof(T)));
-  bool vec = (P.hw % PX == 0) && aligned16(in) && aligned16(out) &&
+  bool vec = (P.hw % PX == 0) && (P.W % PX == 0) && aligned16(in) && aligned16(out) &&
              (!(MASK & ST_GRAIN) || P.ext_noise == nullptr || aligned16(P.ext_noise));
   if (vec) return launch_point_k<T, MASK, EXACT, true>(in, out, P, ctx);
   return launch_point_k<T, MASK, EXACT, false>(in, out, P, ctx);

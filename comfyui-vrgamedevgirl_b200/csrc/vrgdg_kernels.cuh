@@ -16,7 +16,6 @@
 namespace vrgdg {
 
 enum { ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4 };
-constexpr int PHILOX_ROUNDS = 10;
 
 // ---- element conversion -------------------------------------------------------------------------
 template <typename T> struct Elem;
@@ -42,6 +41,7 @@ struct PointParams {
   uint64_t seed;
   int64_t frame0;
   int seed_mode;
+  GrainKey gkey;               // Philox round keys, evaluated on the host
   const void* ext_noise;       // [B,H,W,3] of the frame dtype, or null
   // colour match
   const float* cm_params;      // [B][12]
@@ -50,16 +50,11 @@ struct PointParams {
   LutParams lut;
 };
 
-// One pixel through the enabled stages.  nz* = external noise (used when has_ext).
+// One pixel through the enabled stages; (zr,zg,zb) = this pixel's N(0,1) triple (generator or external).
 template <int MASK, bool EXACT>
-__device__ __forceinline__ void process_pixel(const PointParams& P, const GrainKey& gk, const float* cmp,
-                                              uint32_t pix_in_frame, bool has_ext,
-                                              float nzr, float nzg, float nzb,
+__device__ __forceinline__ void process_pixel(const PointParams& P, const float* cmp, float zr, float zg, float zb,
                                               float& r, float& g, float& b) {
   if (MASK & ST_GRAIN) {
-    float zr, zg, zb;
-    if (has_ext) { zr = nzr; zg = nzg; zb = nzb; }
-    else grain_normals<PHILOX_ROUNDS>(gk, pix_in_frame, zr, zg, zb);
     if (EXACT) grain_blend_exact(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
     else grain_blend_fast(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
   }
@@ -86,17 +81,20 @@ template <typename T, int MASK, bool EXACT, bool VEC>
 __global__ void __launch_bounds__(256)
 k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         int blocks_per_frame, int64_t total_vblocks) {
-  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;
+  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;   // VEC additionally requires W % PX == 0 (a group never wraps a row)
   constexpr int NE = PX * 3;
-  const bool has_ext = (MASK & ST_GRAIN) && (P.ext_noise != nullptr);
+  constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
+  const bool has_ext = GRAIN && (P.ext_noise != nullptr);
   for (int64_t vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const int frame = (int)(vb / blocks_per_frame);
     const int bif = (int)(vb - (int64_t)frame * blocks_per_frame);
     const int64_t pix0 = ((int64_t)bif * 256 + threadIdx.x) * PX;
     if (pix0 >= P.hw) continue;
     const int64_t e0 = ((int64_t)frame * P.hw + pix0) * 3;
-    GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+    const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
     const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
+    const uint32_t y = GRAIN ? (uint32_t)pix0 / (uint32_t)P.W : 0u;
+    const uint32_t x = GRAIN ? (uint32_t)pix0 - y * (uint32_t)P.W : 0u;
 
     float v[NE];
     float nz[NE];
@@ -122,19 +120,34 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         for (int i = 0; i < NE; ++i) nz[i] = Elem<T>::ld(ns[i]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < PX; ++j) {
-      process_pixel<MASK, EXACT>(P, gk, cmp, (uint32_t)(pix0 + j), has_ext,
-                                 has_ext ? nz[3 * j] : 0.f, has_ext ? nz[3 * j + 1] : 0.f,
-                                 has_ext ? nz[3 * j + 2] : 0.f, v[3 * j], v[3 * j + 1], v[3 * j + 2]);
-    }
     if (VEC) {
+      // x is a multiple of PX (even): PX/2 whole generator pairs
+#pragma unroll
+      for (int j = 0; j < PX; j += 2) {
+        float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (GRAIN) {
+          if (has_ext) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) z[i] = nz[3 * j + i];
+          } else {
+            grain_pair_normals(grain_pair_bits(P.gkey, gf, (x >> 1) + (uint32_t)(j >> 1), y), z);
+          }
+        }
+        process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+        process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], v[3 * j + 3], v[3 * j + 4], v[3 * j + 5]);
+      }
       union { uint4 q[3]; T e[NE]; } u;
 #pragma unroll
       for (int i = 0; i < NE; ++i) u.e[i] = Elem<T>::st(v[i]);
       uint4* dst = reinterpret_cast<uint4*>(out + e0);
       dst[0] = u.q[0]; dst[1] = u.q[1]; dst[2] = u.q[2];
     } else {
+      float zr = 0.f, zg = 0.f, zb = 0.f;
+      if (GRAIN) {
+        if (has_ext) { zr = nz[0]; zg = nz[1]; zb = nz[2]; }
+        else grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
+      }
+      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2]);
 #pragma unroll
       for (int i = 0; i < NE; ++i) out[e0 + i] = Elem<T>::st(v[i]);
     }
@@ -164,14 +177,15 @@ k_lut_rgba(const T* __restrict__ in, T* __restrict__ out, int64_t npix, LutParam
 
 // raw normals of the generator, [B,H,W,3] fp32
 static __global__ void __launch_bounds__(256)
-k_grain_noise(float* __restrict__ out, int B, int64_t hw, uint64_t seed, int64_t frame0, int seed_mode) {
+k_grain_noise(float* __restrict__ out, int B, int W, int64_t hw, uint64_t seed, int64_t frame0, int seed_mode, GrainKey K) {
   const int64_t total = (int64_t)B * hw;
   for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
     int frame = (int)(p / hw);
     uint32_t pif = (uint32_t)(p - (int64_t)frame * hw);
-    GrainKey gk = grain_key(seed, frame0, frame, seed_mode);
+    uint32_t y = pif / (uint32_t)W, x = pif - y * (uint32_t)W;
+    GrainFrame gf = grain_frame(seed, frame0, frame, seed_mode);
     float zr, zg, zb;
-    grain_normals<PHILOX_ROUNDS>(gk, pif, zr, zg, zb);
+    grain_pixel_normals(K, gf, x, y, zr, zg, zb);
     out[p * 3] = zr; out[p * 3 + 1] = zg; out[p * 3 + 2] = zb;
   }
 }
@@ -228,6 +242,7 @@ struct TileParams {
   uint64_t pseed;
   int64_t pframe0;
   int pseed_mode;
+  GrainKey pkey;                // round keys of the post-grain generator
   int use_tma;                  // 0: cooperative bounds-checked loads (any alignment)
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
 };
@@ -243,6 +258,7 @@ template <typename T> struct TileCfg {
   static constexpr int RG = 240 / COLS;               // row groups (240 active threads of 256)
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
+  static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
   static constexpr int NS = 3;                        // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
@@ -307,6 +323,47 @@ __device__ __forceinline__ void load_window(const E* rowp /* -> tile column PADL
   }
 }
 
+// grain after the stencil (EnhancerNodes.py:285-293) on VEC consecutive row elements starting at element ge0
+template <int VEC>
+__device__ __forceinline__ void post_grain_elems(const TileParams& Q, const GrainFrame& gf, int ge0, int y, float* o) {
+  const int pfirst = ge0 / 3, plast = (ge0 + VEC - 1) / 3;
+  constexpr int NPR = (VEC + 1) / 3 + 1;                    // pixel pairs a run of VEC elements can touch
+#pragma unroll
+  for (int q = 0; q < NPR; ++q) {
+    const int pair = (pfirst >> 1) + q;
+    if (pair * 2 > plast) break;
+    float z[6];
+    grain_pair_normals(grain_pair_bits(Q.pkey, gf, (uint32_t)pair, (uint32_t)y), z);
+    const float gy0 = Q.poms * z[1], gy1 = Q.poms * z[4];
+    const float g0 = fmaf(2.0f * Q.ps, z[0], gy0), g1 = fmaf(Q.ps, z[1], gy0), g2 = fmaf(3.0f * Q.ps, z[2], gy0);
+    const float g3 = fmaf(2.0f * Q.ps, z[3], gy1), g4 = fmaf(Q.ps, z[4], gy1), g5 = fmaf(3.0f * Q.ps, z[5], gy1);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int idx = ge0 + e - pair * 6;                   // 0..5 inside this pair
+      if (idx >= 0 && idx < 6) {
+        const float gv = (idx < 3) ? ((idx == 0) ? g0 : ((idx == 1) ? g1 : g2)) : ((idx == 3) ? g3 : ((idx == 4) ? g4 : g5));
+        o[e] = clamp01(fmaf(Q.pI, gv, o[e]));
+      }
+    }
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParams& Q, int frame, int y, int ge0, const float* o) {
+  if (y < Q.H && ge0 < Q.RW) {
+    T* dst = out + ((int64_t)frame * Q.H + y) * Q.RW + ge0;
+    if (Q.vec_store) {
+      union { uint4 q; T e[VEC]; } u;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
+      *reinterpret_cast<uint4*>(dst) = u.q;
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) if (ge0 + e < Q.RW) dst[e] = Elem<T>::st(o[e]);
+    }
+  }
+}
+
 template <typename T, int OP, bool WORK>
 __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
                                              int frame, int y0, int x0e) {
@@ -318,60 +375,55 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
   const int f0 = cx * VEC;
   const int ge0 = x0e + f0;                 // first output element in the row
   const int rbase = rg * C::RPT;            // first output row of this thread == smem row of its upper neighbour
-  float w[3][WN];
   auto load_row = [&](int srow, float* dst) {
     if (WORK) load_window<float, VEC>(work + srow * BX + PADL + f0, dst);
     else load_window<T, VEC>(raw + srow * BX + PADL + f0, dst);
   };
-  load_row(rbase, w[0]);
-  load_row(rbase + 1, w[1]);
-  GrainKey pk = grain_key(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
+  const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
+  if (OP == 1) {
+    // 3x3 box is separable: keep the horizontal 3-sums of the two previous rows (nodes.py:194-206)
+    float h0[VEC], h1[VEC], c1[VEC], wr[WN];
+    load_row(rbase, wr);
 #pragma unroll
-  for (int j = 0; j < C::RPT; ++j) {
-    load_row(rbase + j + 2, w[2]);
-    const int y = y0 + rbase + j;
-    float o[VEC];
+    for (int e = 0; e < VEC; ++e) h0[e] = (wr[e] + wr[e + 3]) + wr[e + 6];
+    load_row(rbase + 1, wr);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      float n[9] = {w[0][e], w[0][e + 3], w[0][e + 6], w[1][e], w[1][e + 3], w[1][e + 6],
-                    w[2][e], w[2][e + 3], w[2][e + 6]};
-      o[e] = stencil_epilogue(OP, n, Q.strength);
-    }
-    if (Q.post_enabled) {
-      // grain after the stencil (EnhancerNodes.py:285-293); element -> (pixel, channel)
-      const int pfirst = ge0 / 3;
-      constexpr int NPQ = (VEC + 4) / 3;
+    for (int e = 0; e < VEC; ++e) { h1[e] = (wr[e] + wr[e + 3]) + wr[e + 6]; c1[e] = wr[e + 3]; }
 #pragma unroll
-      for (int q = 0; q < NPQ; ++q) {
-        const int px = pfirst + q;
-        float zr, zg, zb;
-        grain_normals<PHILOX_ROUNDS>(pk, (uint32_t)y * (uint32_t)Q.W + (uint32_t)px, zr, zg, zb);
-        const float gy = Q.poms * zg;
-        const float g0 = fmaf(2.0f * Q.ps, zr, gy), g1 = fmaf(Q.ps, zg, gy), g2 = fmaf(3.0f * Q.ps, zb, gy);
+    for (int j = 0; j < C::RPT; ++j) {
+      load_row(rbase + j + 2, wr);
+      const int y = y0 + rbase + j;
+      float o[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const int ch = ge0 + e - px * 3;
-          if (ch >= 0 && ch < 3) {
-            const float gv = (ch == 0) ? g0 : ((ch == 1) ? g1 : g2);
-            o[e] = clamp01(fmaf(Q.pI, gv, o[e]));
-          }
-        }
+      for (int e = 0; e < VEC; ++e) {
+        const float h2 = (wr[e] + wr[e + 3]) + wr[e + 6];
+        const float blur = ((h0[e] + h1[e]) + h2) * 0.1111111111111111f;      // sum / 9.0 to within 1 ulp
+        o[e] = clamp01(fmaf(Q.strength, c1[e] - blur, c1[e]));                 // img + s*(img - blur)
+        h0[e] = h1[e]; h1[e] = h2; c1[e] = wr[e + 3];
       }
+      if (Q.post_enabled) post_grain_elems<VEC>(Q, pgf, ge0, y, o);
+      store_elems<T, VEC>(out, Q, frame, y, ge0, o);
     }
-    if (y < Q.H && ge0 < Q.RW) {
-      T* dst = out + ((int64_t)frame * Q.H + y) * Q.RW + ge0;
-      if (Q.vec_store) {
-        union { uint4 q; T e[VEC]; } u;
+  } else {
+    float w[3][WN];
+    load_row(rbase, w[0]);
+    load_row(rbase + 1, w[1]);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
-        *reinterpret_cast<uint4*>(dst) = u.q;
-      } else {
+    for (int j = 0; j < C::RPT; ++j) {
+      load_row(rbase + j + 2, w[2]);
+      const int y = y0 + rbase + j;
+      float o[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) if (ge0 + e < Q.RW) dst[e] = Elem<T>::st(o[e]);
+      for (int e = 0; e < VEC; ++e) {
+        float n[9] = {w[0][e], w[0][e + 3], w[0][e + 6], w[1][e], w[1][e + 3], w[1][e + 6],
+                      w[2][e], w[2][e + 3], w[2][e + 6]};
+        o[e] = stencil_epilogue(OP, n, Q.strength);
       }
-    }
+      if (Q.post_enabled) post_grain_elems<VEC>(Q, pgf, ge0, y, o);
+      store_elems<T, VEC>(out, Q, frame, y, ge0, o);
 #pragma unroll
-    for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
+      for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
+    }
   }
 }
 
@@ -449,32 +501,51 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     }
 
     // ---- per-pixel pre-stages over the halo tile (grain / colour match / LUT), result in fp32 ----
+    // one task = one generator pixel pair (2 horizontally adjacent pixels): one Philox call, two independent LUT gathers in flight
     if (MASK != 0) {
       const PointParams& P = Q.P;
-      GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+      constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
+      const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
-      const bool has_ext = (MASK & ST_GRAIN) && (P.ext_noise != nullptr);
-      const int px0 = x0e / 3 - 1;
-      for (int i = tid; i < ROWS * C::PPR; i += 256) {
-        int r = i / C::PPR, kx = i - r * C::PPR;
-        int y = y0 - 1 + r, px = px0 + kx;
-        int so = r * BX + PADL - 3 + 3 * kx;
-        bool inside = (y >= 0 && y < Q.H && px >= 0 && px < Q.W);
-        float cr = 0.f, cg = 0.f, cb = 0.f;
-        if (inside) {
-          cr = Elem<T>::ld(raw[so]); cg = Elem<T>::ld(raw[so + 1]); cb = Elem<T>::ld(raw[so + 2]);
-          uint32_t pif = (uint32_t)y * (uint32_t)Q.W + (uint32_t)px;
-          float nr = 0.f, ng = 0.f, nb = 0.f;
-          if (has_ext) {
-            const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
-            nr = Elem<T>::ld(ns[0]); ng = Elem<T>::ld(ns[1]); nb = Elem<T>::ld(ns[2]);
+      const bool has_ext = GRAIN && (P.ext_noise != nullptr);
+      const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
+      for (int i = tid; i < ROWS * C::PAIRS; i += 256) {
+        const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
+        const int y = y0 - 1 + r, pair = pair0 + kx;
+        const int pxa = pair * 2;
+        const int so = r * BX + PADL - 6 + 6 * kx;          // smem element of pixel a (outside the box for kx == 0)
+        const bool rowin = (y >= 0 && y < Q.H);
+        const bool need_a = (kx > 0), need_b = (kx < C::PAIRS - 1);
+        const bool in_a = need_a && rowin && pxa >= 0 && pxa < Q.W;
+        const bool in_b = need_b && rowin && pxa + 1 >= 0 && pxa + 1 < Q.W;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (in_a | in_b) {
+          float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (GRAIN) {
+            if (has_ext) {
+              const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + (int64_t)y * Q.W + pxa) * 3;
+              if (in_a) { z[0] = Elem<T>::ld(ns[0]); z[1] = Elem<T>::ld(ns[1]); z[2] = Elem<T>::ld(ns[2]); }
+              if (in_b) { z[3] = Elem<T>::ld(ns[3]); z[4] = Elem<T>::ld(ns[4]); z[5] = Elem<T>::ld(ns[5]); }
+            } else {
+              grain_pair_normals(grain_pair_bits(P.gkey, gf, (uint32_t)pair, (uint32_t)y), z);
+            }
           }
-          process_pixel<MASK, EXACT>(P, gk, cmp, pif, has_ext, nr, ng, nb, cr, cg, cb);
+          if (in_a) {
+            a0 = Elem<T>::ld(raw[so]); a1 = Elem<T>::ld(raw[so + 1]); a2 = Elem<T>::ld(raw[so + 2]);
+            process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], a0, a1, a2);
+          }
+          if (in_b) {
+            b0 = Elem<T>::ld(raw[so + 3]); b1 = Elem<T>::ld(raw[so + 4]); b2 = Elem<T>::ld(raw[so + 5]);
+            process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], b0, b1, b2);
+          }
         }
-        if (WORK) { work[so] = cr; work[so + 1] = cg; work[so + 2] = cb; }
-        else if (inside) {
+        if (WORK) {
+          if (need_a) { work[so] = a0; work[so + 1] = a1; work[so + 2] = a2; }
+          if (need_b) { work[so + 3] = b0; work[so + 4] = b1; work[so + 5] = b2; }
+        } else {
           float* rf = reinterpret_cast<float*>(raw);
-          rf[so] = cr; rf[so + 1] = cg; rf[so + 2] = cb;
+          if (in_a) { rf[so] = a0; rf[so + 1] = a1; rf[so + 2] = a2; }
+          if (in_b) { rf[so + 3] = b0; rf[so + 4] = b1; rf[so + 5] = b2; }
         }
       }
       __syncthreads();
@@ -520,7 +591,7 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
   const int frame = blockIdx.y;
   const int64_t pbeg = (int64_t)row0 * P.W, n = (int64_t)rows * P.W;
   const T* fbase = in + (int64_t)frame * P.hw * 3;
-  GrainKey gk = grain_key(P.seed, P.frame0, frame, P.seed_mode);
+  const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
   const bool has_ext = GRAIN && (P.ext_noise != nullptr);
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -532,9 +603,11 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
       if (has_ext) {
         const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
         nr = Elem<T>::ld(ns[0]); ng = Elem<T>::ld(ns[1]); nb = Elem<T>::ld(ns[2]);
-        process_pixel<ST_GRAIN, true>(P, gk, nullptr, (uint32_t)pif, true, nr, ng, nb, r, g, b);
+        process_pixel<ST_GRAIN, true>(P, nullptr, nr, ng, nb, r, g, b);
       } else {
-        process_pixel<ST_GRAIN, false>(P, gk, nullptr, (uint32_t)pif, false, 0.f, 0.f, 0.f, r, g, b);
+        const uint32_t y = (uint32_t)pif / (uint32_t)P.W, x = (uint32_t)pif - y * (uint32_t)P.W;
+        grain_pixel_normals(P.gkey, gf, x, y, nr, ng, nb);
+        process_pixel<ST_GRAIN, false>(P, nullptr, nr, ng, nb, r, g, b);
       }
     }
     float L, A, Bv;

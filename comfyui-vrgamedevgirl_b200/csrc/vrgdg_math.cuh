@@ -50,83 +50,127 @@ VRGDG_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
 #endif
 }
 
-template <int ROUNDS>
-VRGDG_HD U4 philox4x32(U4 c, uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+constexpr int PHILOX_ROUNDS = 10;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+// Round keys are a function of the key only -> evaluated once on the host and read from the kernel's constant
+// bank (no registers, no per-pixel key schedule).
+struct GrainKey {
+  uint32_t rk[PHILOX_ROUNDS][2];
+};
+
+VRGDG_HD U4 philox4x32_rk(U4 c, const GrainKey& K) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     uint32_t h0, l0, h1, l1;
     mulhilo(M0, c.x, h0, l0);
     mulhilo(M1, c.z, h1, l1);
     U4 n;
-    n.x = h1 ^ c.y ^ k0;
+    n.x = h1 ^ c.y ^ K.rk[r][0];
     n.y = l1;
-    n.z = h0 ^ c.w ^ k1;
+    n.z = h0 ^ c.w ^ K.rk[r][1];
     n.w = l0;
     c = n;
-    k0 += W0;
-    k1 += W1;
   }
   return c;
 }
 
-// Key/counter layout of the grain generator (documented in DESIGN.md):
-//   key     = (seed_lo, seed_hi)
-//   counter = (pixel index inside the frame, 0x5652 "VR", frame_lo, frame_hi)
-struct GrainKey {
-  uint32_t k0, k1;     // Philox key
-  uint32_t f0, f1;     // frame part of the counter
-};
+// Grain generator (documented in DESIGN.md).  One Philox call serves a horizontal PIXEL PAIR (x>>1):
+//   counter = (x >> 1, y, fw0, fw1), key -> round keys K
+//   VRGDG_SEED_PER_CLIP : key = (seed_lo, seed_hi);            (fw0, fw1) = absolute frame index frame0+i
+//   VRGDG_SEED_PER_FRAME: key = ("VRGD", "B200") constants;    (fw0, fw1) = ((seed+frame0+i) & 0x7FFFFFFF, 0xFFFFFFFF)
+//                         (EnhancerNodes.py:267-268 seeds one generator per frame with exactly that value)
+// The 128 output bits are cut into six 21-bit fields = three Box-Muller (radius, angle) pairs = six normals:
+//   pixel 0 of the pair: z_r, z_g = pair A (cos, sin), z_b = pair B (cos);  pixel 1: z_r = pair B (sin), z_g, z_b = pair C.
+inline void grain_make_key(uint64_t seed, int seed_mode, GrainKey& K) {
+  uint32_t k0 = (seed_mode == 1) ? 0x56524744u : (uint32_t)seed;
+  uint32_t k1 = (seed_mode == 1) ? 0x42323030u : (uint32_t)(seed >> 32);
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
+    K.rk[r][0] = k0 + (uint32_t)r * PHILOX_W0;
+    K.rk[r][1] = k1 + (uint32_t)r * PHILOX_W1;
+  }
+}
 
-VRGDG_HD GrainKey grain_key(uint64_t seed, int64_t frame0, int64_t frame_in_batch, int seed_mode) {
-  GrainKey g;
-  if (seed_mode == 1) {  // VRGDG_SEED_PER_FRAME: EnhancerNodes.py:267-268
-    uint64_t s = (uint64_t)((int64_t)seed + frame0 + frame_in_batch) & 0x7FFFFFFFull;
-    g.k0 = (uint32_t)s; g.k1 = 0u; g.f0 = 0u; g.f1 = 0u;
+struct GrainFrame { uint32_t f0, f1; };
+
+VRGDG_HD GrainFrame grain_frame(uint64_t seed, int64_t frame0, int64_t frame_in_batch, int seed_mode) {
+  GrainFrame g;
+  if (seed_mode == 1) {
+    g.f0 = (uint32_t)((uint64_t)((int64_t)seed + frame0 + frame_in_batch) & 0x7FFFFFFFull);
+    g.f1 = 0xFFFFFFFFu;
   } else {
     uint64_t f = (uint64_t)(frame0 + frame_in_batch);
-    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
-    g.f0 = (uint32_t)f; g.f1 = (uint32_t)(f >> 32);
+    g.f0 = (uint32_t)f;
+    g.f1 = (uint32_t)(f >> 32);
   }
   return g;
 }
 
-// Three N(0,1) per pixel from one Philox call: Box-Muller pair (x,y) -> z_r, z_g; (z,w) -> z_b.
-VRGDG_HD void box_muller3(U4 r, float& zr, float& zg, float& zb) {
-  const float TWO_NEG32 = 2.3283064365386963e-10f;       // 2^-32
-  const float HALF_ULP = 1.1641532182693481e-10f;        // 2^-33 keeps u1 > 0
-  const float TWO_PI_2NEG32 = 1.4629180792671596e-9f;    // 2*pi*2^-32
-  float u1a = fmaf((float)r.x, TWO_NEG32, HALF_ULP);
-  float u1b = fmaf((float)r.z, TWO_NEG32, HALF_ULP);
-  float tha = (float)r.y * TWO_PI_2NEG32;
-  float thb = (float)r.w * TWO_PI_2NEG32;
-#if defined(__CUDA_ARCH__)
-  // -2 ln u = -2 ln2 * log2 u ; MUFU.LG2, MUFU.SQRT, MUFU.SIN/COS
-  float la = __log2f(u1a) * -1.3862943611198906f;
-  float lb = __log2f(u1b) * -1.3862943611198906f;
-  float ra, rb;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(la));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(lb));
-  float sa, ca;
-  __sincosf(tha, &sa, &ca);
-  float cb = __cosf(thb);
-#else
-  float ra = sqrtf(-2.0f * logf(u1a));
-  float rb = sqrtf(-2.0f * logf(u1b));
-  float sa = sinf(tha), ca = cosf(tha);
-  float cb = cosf(thb);
-#endif
-  zr = ra * ca;
-  zg = ra * sa;
-  zb = rb * cb;
+VRGDG_HD U4 grain_pair_bits(const GrainKey& K, const GrainFrame& f, uint32_t xpair, uint32_t y) {
+  U4 c;
+  c.x = xpair; c.y = y; c.z = f.f0; c.w = f.f1;
+  return philox4x32_rk(c, K);
 }
 
-template <int ROUNDS>
-VRGDG_HD void grain_normals(const GrainKey& g, uint32_t pixel_in_frame, float& zr, float& zg, float& zb) {
-  U4 c;
-  c.x = pixel_in_frame; c.y = 0x5652u; c.z = g.f0; c.w = g.f1;
-  U4 r = philox4x32<ROUNDS>(c, g.k0, g.k1);
-  box_muller3(r, zr, zg, zb);
+// Box-Muller on 21-bit fields: u = (k + 0.5) 2^-21 in (0,1), theta = 2 pi k 2^-21
+VRGDG_HD void box_muller21(uint32_t rad, uint32_t ang, float& c, float& s) {
+  const float S21 = 4.76837158203125e-07f;              // 2^-21
+  const float H21 = 2.384185791015625e-07f;             // 2^-22
+  const float TWO_PI_S21 = 2.9960562263390644e-06f;     // 2 pi 2^-21
+  float u = fmaf((float)rad, S21, H21);
+  float th = (float)ang * TWO_PI_S21;
+#if defined(__CUDA_ARCH__)
+  // -2 ln u = -2 ln2 log2 u : MUFU.LG2, MUFU.SQRT, MUFU.SIN, MUFU.COS
+  float l2, rr, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(l2 * -1.3862943611198906f));
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(th));
+#else
+  float rr = sqrtf(-2.0f * logf(u));
+  float sn = sinf(th), cs = cosf(th);
+#endif
+  c = rr * cs;
+  s = rr * sn;
+}
+
+VRGDG_HD void grain_fields(U4 r, uint32_t* rad, uint32_t* ang) {
+  const uint32_t M = 0x1FFFFFu;
+  rad[0] = r.x & M;
+  ang[0] = ((r.x >> 21) | (r.y << 11)) & M;
+  rad[1] = (r.y >> 10) & M;
+  ang[1] = r.z & M;
+  rad[2] = ((r.z >> 21) | (r.w << 11)) & M;
+  ang[2] = (r.w >> 10) & M;
+}
+
+// all six normals of a pair: z[0..2] = pixel 0 (r,g,b), z[3..5] = pixel 1
+VRGDG_HD void grain_pair_normals(U4 r, float* z) {
+  uint32_t rad[3], ang[3];
+  grain_fields(r, rad, ang);
+  float c0, s0, c1, s1, c2, s2;
+  box_muller21(rad[0], ang[0], c0, s0);
+  box_muller21(rad[1], ang[1], c1, s1);
+  box_muller21(rad[2], ang[2], c2, s2);
+  z[0] = c0; z[1] = s0; z[2] = c1;
+  z[3] = s1; z[4] = c2; z[5] = s2;
+}
+
+// the three normals of one pixel of the pair (lane = x & 1): two Box-Muller evaluations
+VRGDG_HD void grain_lane_normals(U4 r, int lane, float& zr, float& zg, float& zb) {
+  uint32_t rad[3], ang[3];
+  grain_fields(r, rad, ang);
+  float c1, s1, ca, sa;
+  box_muller21(rad[1], ang[1], c1, s1);
+  box_muller21(lane ? rad[2] : rad[0], lane ? ang[2] : ang[0], ca, sa);
+  zr = lane ? s1 : ca;
+  zg = lane ? ca : sa;
+  zb = lane ? sa : c1;
+}
+
+VRGDG_HD void grain_pixel_normals(const GrainKey& K, const GrainFrame& f, uint32_t x, uint32_t y, float& zr, float& zg, float& zb) {
+  grain_lane_normals(grain_pair_bits(K, f, x >> 1, y), (int)(x & 1u), zr, zg, zb);
 }
 
 // ---- grain blend: nodes.py:53-60 ------------------------------------------------------------
@@ -160,6 +204,7 @@ struct LutParams {
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
   float blend, one_minus_blend;
+  int unit_domain;       // dmin == 0 and dspan == 1: (x-0)/1 == x exactly, the division is skipped
 };
 
 #if defined(__CUDA_ARCH__)
@@ -169,8 +214,8 @@ struct LutParams {
 #endif
 
 // coordinate -> (cell index, fraction); bit-exact with :296-316
-VRGDG_HD void lut_coord(float v, float dmin, float dspan, float smax, int S, int& i0, int& i1, float& f) {
-  float n = divx(subx(v, dmin), dspan);          // (source - domain_min) / domain_span
+VRGDG_HD void lut_coord(float v, float dmin, float dspan, bool unit, float smax, int S, int& i0, int& i1, float& f) {
+  float n = unit ? v : divx(subx(v, dmin), dspan);   // (source - domain_min) / domain_span
   n = clamp01(n);                                 // torch.clamp(normalized, 0, 1)
   float c = mulx(n, smax);                        // normalized * max_index
   float fl = floorf(c);
@@ -189,9 +234,9 @@ template <bool EXACT>
 VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   int r0, r1, g0, g1, b0, b1;
   float fr, fg, fb;
-  lut_coord(r, P.dmin[0], P.dspan[0], P.smax, P.S, r0, r1, fr);
-  lut_coord(g, P.dmin[1], P.dspan[1], P.smax, P.S, g0, g1, fg);
-  lut_coord(b, P.dmin[2], P.dspan[2], P.smax, P.S, b0, b1, fb);
+  lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
+  lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
+  lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
   const int S = P.S;
   const float* L = P.lut;
   // element offsets of the 8 corners: ((b*S+g)*S+r)*3

@@ -10,13 +10,32 @@ extern "C" {
 
 void hc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   U4 c{ctr[0], ctr[1], ctr[2], ctr[3]};
-  U4 r = philox4x32<10>(c, key[0], key[1]);
+  GrainKey K;
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) { K.rk[r][0] = key[0] + (uint32_t)r * PHILOX_W0; K.rk[r][1] = key[1] + (uint32_t)r * PHILOX_W1; }
+  U4 r = philox4x32_rk(c, K);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
-void hc_normals(uint64_t seed, int64_t frame0, int64_t frame, int mode, uint32_t pix0, int64_t n, float* out) {
-  GrainKey gk = grain_key(seed, frame0, frame, mode);
-  for (int64_t i = 0; i < n; ++i) grain_normals<10>(gk, pix0 + (uint32_t)i, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+// normals of a W-wide frame region: rows [y0, y0+rows), all x; out [rows][W][3]
+void hc_normals(uint64_t seed, int64_t frame0, int64_t frame, int mode, int W, int y0, int rows, float* out) {
+  GrainKey K;
+  grain_make_key(seed, mode, K);
+  GrainFrame gf = grain_frame(seed, frame0, frame, mode);
+  for (int y = 0; y < rows; ++y)
+    for (int x = 0; x < W; ++x) {
+      float* o = out + ((int64_t)y * W + x) * 3;
+      grain_pixel_normals(K, gf, (uint32_t)x, (uint32_t)(y0 + y), o[0], o[1], o[2]);
+    }
+}
+
+// same region through the pair interface (what the vector kernels use); W must be even
+void hc_normals_pairs(uint64_t seed, int64_t frame0, int64_t frame, int mode, int W, int y0, int rows, float* out) {
+  GrainKey K;
+  grain_make_key(seed, mode, K);
+  GrainFrame gf = grain_frame(seed, frame0, frame, mode);
+  for (int y = 0; y < rows; ++y)
+    for (int xp = 0; xp < W / 2; ++xp)
+      grain_pair_normals(grain_pair_bits(K, gf, (uint32_t)xp, (uint32_t)(y0 + y)), out + ((int64_t)y * W + 2 * xp) * 3);
 }
 
 void hc_grain(const float* in, const float* noise, float* out, int64_t n, float I, float s, float oms, int exact) {
@@ -34,6 +53,7 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
   P.lut = lut; P.S = S; P.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
   P.blend = blend; P.one_minus_blend = omb;
+  P.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f);
   for (int64_t i = 0; i < n; ++i) {
     float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
     float x0 = r, x1 = g, x2 = b;

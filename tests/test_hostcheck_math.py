@@ -32,23 +32,37 @@ def test_philox4x32_10_known_answers(hostcheck):
 
 
 def test_normals_are_standard_and_keyed(hostcheck):
-    hostcheck.hc_normals.argtypes = [ctypes.c_uint64, i64, i64, ci, ctypes.c_uint32, i64, vp]
-    n = 200000
-    a = np.zeros((n, 3), dtype=np.float32)
-    hostcheck.hc_normals(42, 0, 0, 0, 0, n, P(a))
-    assert abs(a.mean()) < 0.01 and abs(a.var() - 1.0) < 0.01 and abs((a ** 4).mean() - 3.0) < 0.1
-    b = np.zeros((n, 3), dtype=np.float32)
-    hostcheck.hc_normals(42, 5, 0, 0, 0, n, P(b))                    # other frame
+    """generator definition: one Philox call per horizontal pixel pair, counter (x>>1, y, frame words)."""
+    sig = [ctypes.c_uint64, i64, i64, ci, ci, ci, ci, vp]
+    hostcheck.hc_normals.argtypes = sig
+    hostcheck.hc_normals_pairs.argtypes = sig
+    W, R = 640, 300
+    a = np.zeros((R, W, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 0, 0, 0, W, 0, R, P(a))
+    assert abs(a.mean()) < 0.01 and abs(a.var() - 1.0) < 0.01 and abs((a.astype(np.float64) ** 4).mean() - 3.0) < 0.1
+    assert np.abs(a).max() > 4.0 and np.abs(a).max() < 5.6           # 21-bit radius field: |z| <= 5.52
+    for c0, c1 in ((0, 1), (0, 2), (1, 2)):
+        assert abs((a[..., c0] * a[..., c1]).mean()) < 0.01
+    assert abs((a[:, :-1, 0] * a[:, 1:, 0]).mean()) < 0.01 and abs((a[:, 0::2, 2] * a[:, 1::2, 0]).mean()) < 0.01   # within a pair too
+    ap = np.zeros_like(a)
+    hostcheck.hc_normals_pairs(42, 0, 0, 0, W, 0, R, P(ap))           # pair interface == per-pixel interface
+    assert np.array_equal(a, ap)
+    b = np.zeros_like(a)
+    hostcheck.hc_normals(42, 5, 0, 0, W, 0, R, P(b))                  # other frame
     assert np.abs(a - b).mean() > 0.5
-    c = np.zeros((10, 3), dtype=np.float32)
-    hostcheck.hc_normals(42, 0, 0, 0, 100, 10, P(c))                 # offset window of the same frame
+    c = np.zeros((10, W, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 0, 0, 0, W, 100, 10, P(c))               # a window of the same frame: counter-based
     assert np.array_equal(c, a[100:110])
-    # PER_FRAME mode: (seed + frame0 + i) & 0x7fffffff is the key -> (40,2,0) == (42,0,0) == (30,5,7)
-    d, e, f = (np.zeros((10, 3), dtype=np.float32) for _ in range(3))
-    hostcheck.hc_normals(40, 2, 0, 1, 0, 10, P(d))
-    hostcheck.hc_normals(42, 0, 0, 1, 0, 10, P(e))
-    hostcheck.hc_normals(30, 5, 7, 1, 0, 10, P(f))
-    assert np.array_equal(d, e) and np.array_equal(e, f)
+    # odd width: same (x, y) -> same value regardless of the frame width
+    d = np.zeros((4, 33, 3), dtype=np.float32)
+    hostcheck.hc_normals(42, 0, 0, 0, 33, 0, 4, P(d))
+    assert np.array_equal(d, a[:4, :33])
+    # PER_FRAME mode: (seed + frame0 + i) & 0x7fffffff is what matters -> (40,2,0) == (42,0,0) == (30,5,7)
+    e, f, g = (np.zeros((4, 64, 3), dtype=np.float32) for _ in range(3))
+    hostcheck.hc_normals(40, 2, 0, 1, 64, 0, 4, P(e))
+    hostcheck.hc_normals(42, 0, 0, 1, 64, 0, 4, P(f))
+    hostcheck.hc_normals(30, 5, 7, 1, 64, 0, 4, P(g))
+    assert np.array_equal(e, f) and np.array_equal(f, g) and not np.array_equal(e, a[:4, :64])
 
 
 def test_grain_blend_exact_is_bit_identical(hostcheck):
