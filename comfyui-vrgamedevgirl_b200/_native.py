@@ -68,6 +68,8 @@ SIGNATURES = {
     "vrgdg_device_info": (_i, [ctypes.POINTER(_i)] * 3),
     "vrgdg_launch_count": (_i64, []),
     "vrgdg_last_tile_path": (ctypes.c_char_p, []),
+    "vrgdg_lut3d_packed_bytes": (_i64, [_i]),
+    "vrgdg_lut3d_pack": (_i, [_vp, _vp, _i, _vp]),
     "vrgdg_lut3d_apply": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i, _fp, _fp, _f, _f, _vp]),
     "vrgdg_grain": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _u64, _i64, _i, _vp, _vp]),
     "vrgdg_grain_noise": (_i, [_vp, _i, _i, _i, _u64, _i64, _i, _vp]),

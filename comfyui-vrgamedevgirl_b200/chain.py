@@ -27,7 +27,7 @@ class PostChain:
         self._lut_dev = None
         self._ref_sums = None
         if lut is not None:
-            self._lut_dev = lut["lut_data"]["lut"].to(device=self.device, dtype=torch.float32).contiguous()
+            self._lut_dev = ops.pack_lut(lut["lut_data"]["lut"], self.device)
         if colormatch is not None:
             self.set_reference(colormatch.get("reference_image"), colormatch.get("ref_sums"))
 
@@ -56,8 +56,8 @@ class PostChain:
                 dmin = data["domain_min"].to(dtype=frames.dtype)
                 span = torch.clamp(data["domain_max"].to(dtype=frames.dtype) - dmin, min=1e-6)
                 d.lut_enabled = 1
-                d.lut = self._lut_dev.data_ptr()
-                d.lut_size = int(self._lut_dev.shape[0])
+                d.lut = self._lut_dev.data.data_ptr()
+                d.lut_size = self._lut_dev.size
                 d.lut_dmin = (ctypes.c_float * 3)(*dmin.float().tolist())
                 d.lut_dspan = (ctypes.c_float * 3)(*span.float().tolist())
                 d.lut_blend, d.lut_one_minus_blend = blend, 1.0 - blend

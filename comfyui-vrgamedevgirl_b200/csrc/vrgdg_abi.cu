@@ -139,6 +139,7 @@ int run_tile(const void* in, void* out, int B, int H, int W, int dtype, TilePara
 int check_lut(const float* lut, int S, const float* dmin, const float* dspan, const char* who) {
   if (!lut || !dmin || !dspan) return fail(VRGDG_E_INVALID, "%s: null LUT / domain pointer", who);
   if (S < 2 || S > 256) return fail(VRGDG_E_INVALID, "%s: LUT size %d outside [2,256]", who, S);
+  if (reinterpret_cast<uintptr_t>(lut) & 31u) return fail(VRGDG_E_ALIGN, "%s: packed LUT must be 32-byte aligned", who);
   return VRGDG_OK;
 }
 
@@ -159,6 +160,26 @@ int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (sm_count) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *sm_count = v; }
   if (cc_major) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *cc_major = v; }
   if (cc_minor) { if ((e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return fail_cuda(e, "attr"); *cc_minor = v; }
+  return VRGDG_OK;
+}
+
+int64_t vrgdg_lut3d_packed_bytes(int lut_size) {
+  if (lut_size < 2 || lut_size > 256) return 0;
+  return (int64_t)lut_size * lut_size * lut_size * 8 * (int64_t)sizeof(float);
+}
+
+int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream) {
+  if (!lut || !packed) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_pack: null pointer");
+  if (lut_size < 2 || lut_size > 256) return fail(VRGDG_E_INVALID, "vrgdg_lut3d_pack: LUT size %d outside [2,256]", lut_size);
+  if (reinterpret_cast<uintptr_t>(packed) & 31u) return fail(VRGDG_E_ALIGN, "vrgdg_lut3d_pack: packed buffer must be 32-byte aligned");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  const int n = lut_size * lut_size * lut_size;
+  k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, lut_size);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lut3d_pack");
   return VRGDG_OK;
 }
 

@@ -24,6 +24,7 @@ static cudaError_t launch_point_k(const void* in, void* out, const PointParams& 
   const int64_t total = (int64_t)bpf * P.B;
   if (total == 0) return cudaSuccess;
   auto kern = k_point<T, MASK, EXACT, VEC>;
+  if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // all of it as L1 for the gather
   static int occ = occupancy_of(kern, 256, 0);
   const int64_t cap = (int64_t)ctx.sms * occ * 4;
   const int grid = (int)std::min<int64_t>(total, cap);
@@ -67,7 +68,7 @@ cudaError_t launch_lut_rgba(const void* in, void* out, int64_t npix, const LutPa
 // ---- k_tile ------------------------------------------------------------------------------------
 template <typename T>
 void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y) {
-  using C = TileCfg<T>;
+  using C = TileCfg<T, false>;     // tile geometry is the same for both thread configurations
   tiles_x = (RW + C::TXE - 1) / C::TXE;
   tiles_y = (H + C::TY - 1) / C::TY;
   box_x = C::BX;
@@ -81,12 +82,14 @@ static cudaError_t launch_tile_k(const CUtensorMap* tmap, const void* in, void* 
   // per device context, so set on every launch (single-process multi-GPU hosts)
   cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return attr;
-  static int occ = occupancy_of(kern, 256, smem);
+  constexpr int NT = TileCfg<T, (MASK != 0)>::THREADS;
+  if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024)) + 1);
+  static int occ = occupancy_of(kern, NT, smem);
   if (Q.total_tiles == 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx.sms * occ);
   CUtensorMap dummy;
   if (!tmap) { memset(&dummy, 0, sizeof(dummy)); tmap = &dummy; }
-  kern<<<grid, 256, smem, ctx.stream>>>(*tmap, reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), Q);
+  kern<<<grid, NT, smem, ctx.stream>>>(*tmap, reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), Q);
   count_launch();
   return cudaGetLastError();
 }

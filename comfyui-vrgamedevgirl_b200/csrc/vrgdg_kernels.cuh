@@ -247,28 +247,33 @@ struct TileParams {
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
 };
 
-template <typename T> struct TileCfg {
+// HEAVY = per-pixel pre-stages enabled: one 512-thread CTA per SM with a 2-stage ring keeps ~150 KB of the SM's
+// 228 KB as L1 for the LUT gather; the pure stencils use 256-thread CTAs, a 3-stage ring and 2 CTAs per SM.
+template <typename T, bool HEAVY> struct TileCfg {
   static constexpr int VEC = 16 / sizeof(T);          // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
   static constexpr int PADL = VEC;                    // box starts PADL elements left of the tile (>= 3)
-  static constexpr int TXE = 240;                     // output elements per tile row (multiple of 3 and of VEC)
+  static constexpr int TXE = 240;                     // output elements per tile row (multiple of 6 and of VEC)
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
+  static constexpr int THREADS = HEAVY ? 512 : 256;
+  static constexpr int MINB = HEAVY ? 1 : 2;
   static constexpr int COLS = TXE / VEC;              // threads across
-  static constexpr int RG = 240 / COLS;               // row groups (240 active threads of 256)
+  static constexpr int RG = (HEAVY ? 480 : 240) / COLS;   // row groups (active threads / COLS)
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
-  static constexpr int NS = 3;                        // pipeline stages
+  static constexpr int NS = HEAVY ? 2 : 3;            // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
-  static_assert(TY % RG == 0, "rows per thread");
+  static_assert(TY % RG == 0 && COLS * RG <= THREADS, "thread mapping");
 };
 
 template <typename T, int MASK>
 constexpr size_t tile_smem_bytes() {
-  size_t s = (size_t)TileCfg<T>::NS * TileCfg<T>::STAGE_BYTES;
-  if (MASK != 0 && sizeof(T) != 4) s += (size_t)TileCfg<T>::ROWS * TileCfg<T>::BX * 4;   // fp32 work tile
+  using C = TileCfg<T, (MASK != 0)>;
+  size_t s = (size_t)C::NS * C::STAGE_BYTES;
+  if (MASK != 0 && sizeof(T) != 4) s += (size_t)C::ROWS * C::BX * 4;   // fp32 work tile
   return s + 64 /* mbarriers */ + 128 /* alignment slack */;
 }
 
@@ -364,10 +369,10 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
   }
 }
 
-template <typename T, int OP, bool WORK>
+template <typename T, int OP, bool WORK, bool HEAVY>
 __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
                                              int frame, int y0, int x0e) {
-  using C = TileCfg<T>;
+  using C = TileCfg<T, HEAVY>;
   constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, WN = VEC + 6;
   const int tid = threadIdx.x;
   if (tid >= C::COLS * C::RG) return;
@@ -428,9 +433,11 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
 }
 
 template <typename T, int MASK, bool EXACT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__((TileCfg<T, (MASK != 0)>::THREADS), (TileCfg<T, (MASK != 0)>::MINB))
 k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __restrict__ out, TileParams Q) {
-  using C = TileCfg<T>;
+  constexpr bool HEAVY = (MASK != 0);
+  using C = TileCfg<T, HEAVY>;
+  constexpr int NT = C::THREADS;
   constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, TXE = C::TXE, TY = C::TY, ROWS = C::ROWS;
   constexpr int NS = C::NS;
   constexpr bool WORK = (MASK != 0) && (sizeof(T) != 4);   // separate fp32 tile for the pre-stage results
@@ -490,7 +497,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     } else {
       // generic loader: zero-filled halo tile, any alignment
       const T* fbase = in + (int64_t)frame * Q.H * Q.RW;
-      for (int i = tid; i < ROWS * BX; i += 256) {
+      for (int i = tid; i < ROWS * BX; i += NT) {
         int r = i / BX, c = i - r * BX;
         int y = y0 - 1 + r, x = x0e - PADL + c;
         T v = Elem<T>::st(0.0f);
@@ -509,7 +516,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
       const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
-      for (int i = tid; i < ROWS * C::PAIRS; i += 256) {
+      for (int i = tid; i < ROWS * C::PAIRS; i += NT) {
         const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
         const int y = y0 - 1 + r, pair = pair0 + kx;
         const int pxa = pair * 2;
@@ -560,12 +567,12 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     {
       const float* wt = WORK ? work : nullptr;
       switch (Q.op) {   // uniform; one specialised row loop per epilogue
-        case 1: stencil_rows<T, 1, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 2: stencil_rows<T, 2, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 3: stencil_rows<T, 3, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 4: stencil_rows<T, 4, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 5: stencil_rows<T, 5, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
-        default: stencil_rows<T, 0, WORK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 1: stencil_rows<T, 1, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 2: stencil_rows<T, 2, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 3: stencil_rows<T, 3, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 4: stencil_rows<T, 4, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 5: stencil_rows<T, 5, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        default: stencil_rows<T, 0, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
       }
     }
     if (tma) fence_proxy_async();   // generic-proxy writes to this stage happen-before its next async refill
@@ -667,6 +674,20 @@ static __global__ void k_colormatch_params(const double* __restrict__ fs, int B,
     double varr = (r[4 + c] - r[1 + c] * mr) / (nr - 1.0);
     p[6 + c] = (float)mr;
     p[9 + c] = __fadd_rn((float)sqrt(varr > 0 ? varr : 0.0), 1e-5f);
+  }
+}
+
+// reference-layout table [S][S][S][3] -> pair table (see vrgdg_math.cuh)
+static __global__ void __launch_bounds__(256)
+k_lut_pack(const float* __restrict__ lut3, float* __restrict__ packed, int S) {
+  const int n = S * S * S;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int r = i % S, g = (i / S) % S, b = i / (S * S);
+    float e[8];
+    lut_pack_entry(lut3, S, b, g, r, e);
+    float4* d = reinterpret_cast<float4*>(packed + (size_t)i * 8);
+    d[0] = make_float4(e[0], e[1], e[2], e[3]);
+    d[1] = make_float4(e[4], e[5], e[6], e[7]);
   }
 }
 

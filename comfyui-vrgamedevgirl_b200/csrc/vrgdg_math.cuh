@@ -8,6 +8,7 @@
 // bit-identical to the reference's CPU tensor ops (each of which rounds once).
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 #include <math.h>
 
 #if defined(__CUDACC__)
@@ -198,8 +199,12 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 }
 
 // ---- 3D LUT trilinear: VRGDG_IV_Adjustments.py:293-336 ------------------------------------------
+// Device table layout ("pair table", built by lut_pack_entry / vrgdg_lut3d_pack):
+//   entry (b,g,r) = { lut[b,g,r,0..2], 0, lut[b,g,min(r+1,S-1),0..2], 0 }   32 bytes, 32-byte aligned
+// so the two red neighbours of a cell edge arrive with ONE 256-bit load (LDG.E.256) and a pixel needs 4 loads
+// instead of 24.  The gather is bound by L1 tag lookups per divergent lane (see profiles/), not by bytes.
 struct LutParams {
-  const float* lut;      // [S][S][S][3], [b][g][r][rgb]
+  const float* lut;      // pair table, S*S*S*8 floats
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -207,11 +212,28 @@ struct LutParams {
   int unit_domain;       // dmin == 0 and dspan == 1: (x-0)/1 == x exactly, the division is skipped
 };
 
+struct F8 { float v[8]; };
+
+VRGDG_HD F8 lut_load_pair(const float* p) {
+  F8 q;
 #if defined(__CUDA_ARCH__)
-#define VRGDG_LDG(p) __ldg(p)
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]), "=f"(q.v[4]), "=f"(q.v[5]), "=f"(q.v[6]), "=f"(q.v[7])
+      : "l"(p));
 #else
-#define VRGDG_LDG(p) (*(p))
+  for (int i = 0; i < 8; ++i) q.v[i] = p[i];
 #endif
+  return q;
+}
+
+// one pair-table entry from the reference-layout table [S][S][S][3]
+VRGDG_HD void lut_pack_entry(const float* lut3, int S, int b, int g, int r, float* dst8) {
+  const int r1 = (r + 1 < S) ? r + 1 : S - 1;
+  const float* a = lut3 + ((size_t)(b * S + g) * S + r) * 3;
+  const float* c = lut3 + ((size_t)(b * S + g) * S + r1) * 3;
+  dst8[0] = a[0]; dst8[1] = a[1]; dst8[2] = a[2]; dst8[3] = 0.0f;
+  dst8[4] = c[0]; dst8[5] = c[1]; dst8[6] = c[2]; dst8[7] = 0.0f;
+}
 
 // coordinate -> (cell index, fraction); bit-exact with :296-316
 VRGDG_HD void lut_coord(float v, float dmin, float dspan, bool unit, float smax, int S, int& i0, int& i1, float& f) {
@@ -227,7 +249,7 @@ VRGDG_HD void lut_coord(float v, float dmin, float dspan, bool unit, float smax,
 template <bool EXACT>
 VRGDG_HD float lerp_ref(float a, float b, float f, float omf) {
   if (EXACT) return addx(mulx(a, omf), mulx(b, f));   // a*(1-f) + b*f, three roundings (:327-335)
-  return fmaf(b, f, a * omf);
+  return fmaf(f, b - a, a);                           // contracted form for fused chains (<= 2e-7 away)
 }
 
 template <bool EXACT>
@@ -237,27 +259,22 @@ VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
   lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
   lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
+  (void)r1;                                         // the red neighbour is the second half of the pair entry
   const int S = P.S;
   const float* L = P.lut;
-  // element offsets of the 8 corners: ((b*S+g)*S+r)*3
-  int ob0g0 = (b0 * S + g0) * S, ob1g0 = (b1 * S + g0) * S;
-  int ob0g1 = (b0 * S + g1) * S, ob1g1 = (b1 * S + g1) * S;
-  const float* p000 = L + (ob0g0 + r0) * 3;   // c000 = lut[b0,g0,r0]
-  const float* p001 = L + (ob1g0 + r0) * 3;   // c001 = lut[b1,g0,r0]
-  const float* p010 = L + (ob0g1 + r0) * 3;   // c010 = lut[b0,g1,r0]
-  const float* p011 = L + (ob1g1 + r0) * 3;   // c011 = lut[b1,g1,r0]
-  const float* p100 = L + (ob0g0 + r1) * 3;   // c100 = lut[b0,g0,r1]
-  const float* p101 = L + (ob1g0 + r1) * 3;
-  const float* p110 = L + (ob0g1 + r1) * 3;
-  const float* p111 = L + (ob1g1 + r1) * 3;
-  float omb = subx(1.0f, fb), omg = subx(1.0f, fg), omr = subx(1.0f, fr);
+  // pair entries of the four (b,g) edges at r0:  v[0..2] = lut[b,g,r0], v[4..6] = lut[b,g,r1]
+  const F8 e00 = lut_load_pair(L + (size_t)((b0 * S + g0) * S + r0) * 8);   // c000 | c100
+  const F8 e01 = lut_load_pair(L + (size_t)((b1 * S + g0) * S + r0) * 8);   // c001 | c101
+  const F8 e10 = lut_load_pair(L + (size_t)((b0 * S + g1) * S + r0) * 8);   // c010 | c110
+  const F8 e11 = lut_load_pair(L + (size_t)((b1 * S + g1) * S + r0) * 8);   // c011 | c111
+  const float omb = subx(1.0f, fb), omg = subx(1.0f, fg), omr = subx(1.0f, fr);
   float o[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float c00 = lerp_ref<EXACT>(VRGDG_LDG(p000 + ch), VRGDG_LDG(p001 + ch), fb, omb);
-    float c01 = lerp_ref<EXACT>(VRGDG_LDG(p010 + ch), VRGDG_LDG(p011 + ch), fb, omb);
-    float c10 = lerp_ref<EXACT>(VRGDG_LDG(p100 + ch), VRGDG_LDG(p101 + ch), fb, omb);
-    float c11 = lerp_ref<EXACT>(VRGDG_LDG(p110 + ch), VRGDG_LDG(p111 + ch), fb, omb);
+    float c00 = lerp_ref<EXACT>(e00.v[ch], e01.v[ch], fb, omb);           // c000*(1-fb) + c001*fb
+    float c01 = lerp_ref<EXACT>(e10.v[ch], e11.v[ch], fb, omb);           // c010, c011
+    float c10 = lerp_ref<EXACT>(e00.v[4 + ch], e01.v[4 + ch], fb, omb);   // c100, c101
+    float c11 = lerp_ref<EXACT>(e10.v[4 + ch], e11.v[4 + ch], fb, omb);   // c110, c111
     float c0 = lerp_ref<EXACT>(c00, c01, fg, omg);
     float c1 = lerp_ref<EXACT>(c10, c11, fg, omg);
     o[ch] = clamp01(lerp_ref<EXACT>(c0, c1, fr, omr));
@@ -273,18 +290,67 @@ VRGDG_HD float lut_blend(float x, float y, float blend, float omb) {
 }
 
 // ---- sRGB <-> CIE Lab (kornia.color restatement; formulas in SURVEY.md §8c) ------------------------
+// The three fractional powers (x^2.4, x^(1/3), x^(1/2.4)) are evaluated as  seed = 2^(e*log2 x)  on the MUFU
+// (~1e-6 relative) followed by ONE Newton step of the matching integer root, which squares the error (result within
+// ~2 ulp of the correctly rounded value; torch.pow itself is ~1 ulp): ~12-16 instructions instead of ~60 for powf.
+VRGDG_HD float approx_pow(float x, float e) {        // x > 0, relative error ~1e-6
+#if defined(__CUDA_ARCH__)
+  float l, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * e));
+  return r;
+#else
+  return exp2f(log2f(x) * e) * (1.0f + 3e-7f);       // host build (tests only): perturbed so that the Newton step is exercised
+#endif
+}
+VRGDG_HD float approx_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// x^(1/3), x in (0, ~2]
+VRGDG_HD float cbrt_pos(float x) {
+  float y = approx_pow(x, 0.33333334f);
+  float y2 = y * y;
+  // Newton: y - (y^3 - x) / (3 y^2)
+  return fmaf(fmaf(-y2, y, x), approx_rcp(3.0f * y2), y);
+}
+// x^0.2
+VRGDG_HD float root5_pos(float x) {
+  float y = approx_pow(x, 0.2f);
+  float y2 = y * y, y4 = y2 * y2;
+  return fmaf(fmaf(-y4, y, x), approx_rcp(5.0f * y4), y);   // y - (y^5 - x) / (5 y^4)
+}
+// x^2.4 = x^2 * (x^0.2)^2
+VRGDG_HD float pow_2p4(float x) {
+  float q = root5_pos(x);
+  return (x * x) * (q * q);
+}
+// x^(1/2.4) = (x^(1/12))^5
+VRGDG_HD float pow_inv2p4(float x) {
+  float y = approx_pow(x, 0.083333336f);
+  float y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y11 = (y8 * y2) * y;
+  y = fmaf(fmaf(-y11, y, x), approx_rcp(12.0f * y11), y);    // y - (y^12 - x) / (12 y^11)
+  y2 = y * y;
+  return (y2 * y2) * y;
+}
+
 VRGDG_HD float srgb_to_linear(float c) {
   // where(c > 0.04045, ((c + 0.055) / 1.055) ** 2.4, c / 12.92)
-  return (c > 0.04045f) ? powf(divx(addx(c, 0.055f), 1.055f), 2.4f) : divx(c, 12.92f);
+  return (c > 0.04045f) ? pow_2p4(divx(addx(c, 0.055f), 1.055f)) : divx(c, 12.92f);
 }
 VRGDG_HD float linear_to_srgb(float l) {
   // where(l > 0.0031308, 1.055 * clamp(l, min=thr) ** (1/2.4) - 0.055, 12.92 * l)
-  return (l > 0.0031308f) ? subx(mulx(1.055f, powf(fmaxf(l, 0.0031308f), (float)(1.0 / 2.4))), 0.055f)
+  return (l > 0.0031308f) ? subx(mulx(1.055f, pow_inv2p4(fmaxf(l, 0.0031308f))), 0.055f)
                           : mulx(12.92f, l);
 }
 VRGDG_HD float lab_f(float t) {
   // where(t > 0.008856, clamp(t, min=0.008856) ** (1/3), 7.787 t + 4/29)
-  return (t > 0.008856f) ? powf(fmaxf(t, 0.008856f), (float)(1.0 / 3.0))
+  return (t > 0.008856f) ? cbrt_pos(fmaxf(t, 0.008856f))
                          : addx(mulx(7.787f, t), (float)(4.0 / 29.0));
 }
 VRGDG_HD void rgb_to_lab(float r, float g, float b, float& L, float& A, float& Bv) {

@@ -142,7 +142,7 @@ def _device_lut(lut_data, dev):
     cache = lut_data.setdefault("_device", {})
     key = str(dev)
     if key not in cache:
-        cache[key] = lut_data["lut"].to(device=dev, dtype=torch.float32).contiguous()
+        cache[key] = ops.pack_lut(lut_data["lut"], dev)      # device layout, built once per (file version, device)
     return cache[key]
 
 
@@ -267,8 +267,7 @@ class VRGDG_LUTS:
         if image.ndim != 4 or image.shape[-1] < 3:
             raise ValueError("VRGDG_LUTS expects IMAGE input shaped like [batch, height, width, channels].")
         span = torch.clamp(domain_max - domain_min, min=1e-6)
-        lut_dev = lut_tensor.to(device=image.device, dtype=torch.float32).contiguous()
-        return ops.lut3d_apply(image, lut_dev, domain_min.float().tolist(), span.float().tolist(), 1.0, 0.0)
+        return ops.lut3d_apply(image, ops.pack_lut(lut_tensor, image.device), domain_min.float().tolist(), span.float().tolist(), 1.0, 0.0)
 
     def apply_lut(self, image, lut_name, device, strength):
         """:345-361"""

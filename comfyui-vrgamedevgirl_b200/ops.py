@@ -18,15 +18,42 @@ def _f32(v):
     return ctypes.c_float(float(v))
 
 
+class PackedLut:
+    """A 3D LUT in the library's device layout (vrgdg_lut3d_pack): `data` float32 [S^3 * 8] on a CUDA device."""
+
+    def __init__(self, data, size):
+        self.data, self.size = data, int(size)
+
+    @property
+    def device(self):
+        return self.data.device
+
+
+def pack_lut(lut, device=None):
+    """[S,S,S,3] float32 table in the reference's [blue][green][red][rgb] order (CPU or CUDA) -> PackedLut."""
+    if isinstance(lut, PackedLut):
+        return lut
+    if not isinstance(lut, torch.Tensor) or lut.ndim != 4 or lut.shape[3] != 3 or not (lut.shape[0] == lut.shape[1] == lut.shape[2]):
+        raise ValueError("vrgdg_b200: lut must be float32 [S,S,S,3]")
+    dev = torch.device(device) if device is not None else lut.device
+    if dev.type != "cuda":
+        raise RuntimeError("vrgdg_b200: LUTs are packed on a CUDA device; there is no CPU path")
+    src = lut.to(device=dev, dtype=torch.float32).contiguous()
+    S = int(src.shape[0])
+    lib = nv.load_library()
+    packed = torch.empty(int(lib.vrgdg_lut3d_packed_bytes(S)) // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nv.check(lib.vrgdg_lut3d_pack(nv.ptr(src), nv.ptr(packed), S, nv.stream_ptr(dev)))
+    return PackedLut(packed, S)
+
+
 def lut3d_apply(image, lut, dmin, dspan, blend=1.0, one_minus_blend=0.0):
-    """VRGDG_LUTS._apply_cube_lut + strength blend.  image [B,H,W,3|4] CUDA; lut [S,S,S,3] fp32 CUDA;
-    dmin / dspan: 3 python floats each (dspan already clamped to >= 1e-6 in the image dtype)."""
+    """VRGDG_LUTS._apply_cube_lut + strength blend.  image [B,H,W,3|4] CUDA; lut: PackedLut (or a [S,S,S,3] fp32 tensor,
+    packed on the fly); dmin / dspan: 3 python floats each (dspan already clamped to >= 1e-6 in the image dtype)."""
     t = nv.require_cuda(image, "image")
     if t.ndim != 4 or t.shape[-1] not in (3, 4):
         raise ValueError("VRGDG_LUTS expects IMAGE input shaped like [batch, height, width, channels].")
-    lut = nv.require_cuda(lut, "lut")
-    if lut.dtype != torch.float32 or lut.ndim != 4 or lut.shape[3] != 3 or not (lut.shape[0] == lut.shape[1] == lut.shape[2]):
-        raise ValueError("vrgdg_b200: lut must be float32 [S,S,S,3]")
+    lut = pack_lut(lut, t.device)
     if lut.device != t.device:
         raise ValueError("vrgdg_b200: lut and image are on different devices")
     out = torch.empty_like(t)
@@ -34,7 +61,7 @@ def lut3d_apply(image, lut, dmin, dspan, blend=1.0, one_minus_blend=0.0):
     lib = nv.load_library()
     with torch.cuda.device(t.device):
         nv.check(lib.vrgdg_lut3d_apply(nv.ptr(t), nv.ptr(out), t.numel() // t.shape[-1], int(t.shape[-1]), nv.DTYPE_CODE[t.dtype],
-                                       nv.ptr(lut), int(lut.shape[0]), c3(*[float(x) for x in dmin]), c3(*[float(x) for x in dspan]),
+                                       nv.ptr(lut.data), lut.size, c3(*[float(x) for x in dmin]), c3(*[float(x) for x in dspan]),
                                        _f32(blend), _f32(one_minus_blend), nv.stream_ptr(t.device)))
     return out
 

@@ -79,13 +79,18 @@ VRGDG_API const char* vrgdg_last_tile_path(void);
 /* ---- 3D LUT, trilinear --------------------------------------------------------------------
  * Replaces VRGDG_LUTS._apply_cube_lut + the strength blend of apply_lut
  * (VRGDG_IV_Adjustments.py:289-343, :355-359; _apply_lut_tensor VRGDG_LUTVideoTools.py:172-185).
- * lut: [S,S,S,3] fp32, index order [blue][green][red][rgb] (:272-274).  dmin/dspan_host: 3 floats
+ * lut_packed: the table in the library's device layout, produced once per LUT by vrgdg_lut3d_pack from the
+ * reference layout [S,S,S,3] fp32, index order [blue][green][red][rgb] (:272-274).  dmin/dspan_host: 3 floats
  * each on the HOST, dspan = clamp(dmax-dmin, 1e-6) already evaluated in the image dtype (:295,:351-352).
  * channels 3 or 4 (alpha copied through, :341-343).  blend in (0,1]: out = in*(1-blend)+lut*blend when
  * blend<1; one_minus_blend is passed separately because the reference forms (1.0-blend) in double.
  * Output is bit-identical to the reference CPU path for fp32 frames. */
+VRGDG_API int64_t vrgdg_lut3d_packed_bytes(int lut_size);
+/* lut: device [S,S,S,3] fp32 (reference layout); packed: device buffer of vrgdg_lut3d_packed_bytes(S), 32-byte aligned.
+ * Entry (b,g,r) of the packed table = {lut[b,g,r,:], 0, lut[b,g,min(r+1,S-1),:], 0}: one 256-bit load per cell edge. */
+VRGDG_API int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream);
 VRGDG_API int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype,
-                      const float* lut, int lut_size,
+                      const float* lut_packed, int lut_size,
                       const float* dmin_host, const float* dspan_host,
                       float blend, float one_minus_blend, void* stream);
 
@@ -140,7 +145,7 @@ typedef struct vrgdg_chain_desc {
   int32_t colormatch_enabled;
   const float* cm_params;
   float cm_t, cm_one_minus_t;
-  /* stage 3: 3D LUT */
+  /* stage 3: 3D LUT (packed table from vrgdg_lut3d_pack) */
   int32_t lut_enabled;
   const float* lut;
   int32_t lut_size;

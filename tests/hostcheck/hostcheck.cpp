@@ -49,8 +49,12 @@ void hc_grain(const float* in, const float* noise, float* out, int64_t n, float 
 
 void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, const float* dmin, const float* dspan,
               float blend, float omb, int exact) {
+  // same packing as vrgdg_lut3d_pack
+  float* packed = new float[(size_t)S * S * S * 8];
+  for (int bb = 0; bb < S; ++bb) for (int gg = 0; gg < S; ++gg) for (int rr = 0; rr < S; ++rr)
+    lut_pack_entry(lut, S, bb, gg, rr, packed + ((size_t)(bb * S + gg) * S + rr) * 8);
   LutParams P;
-  P.lut = lut; P.S = S; P.smax = (float)(S - 1);
+  P.lut = packed; P.S = S; P.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
   P.blend = blend; P.one_minus_blend = omb;
   P.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f);
@@ -64,6 +68,7 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
     }
     out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
   }
+  delete[] packed;
 }
 
 void hc_rgb_to_lab(const float* in, float* out, int64_t n) {
@@ -106,3 +111,7 @@ void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int 
 }
 
 }  // extern "C"
+
+extern "C" void hc_pows(const float* x, float* p24, float* pinv, float* cb, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) { p24[i] = pow_2p4(x[i]); pinv[i] = pow_inv2p4(x[i]); cb[i] = cbrt_pos(x[i]); }
+}

@@ -312,9 +312,9 @@ def test_full_chain_with_colormatch_vs_reference_composition(pkg, cuda_device):
     d.grain_enabled, d.grain_intensity, d.grain_sat, d.grain_one_minus_sat = 1, 0.04, 0.5, 0.5
     d.colormatch_enabled, d.cm_params, d.cm_t, d.cm_one_minus_t = 1, params.data_ptr(), 1.0, 0.0
     lut = _lut33(pkg)
-    lut_dev = lut["lut"].to(cuda_device)
+    lut_dev = pkg.ops.pack_lut(lut["lut"], cuda_device)
     import ctypes
-    d.lut_enabled, d.lut, d.lut_size = 1, lut_dev.data_ptr(), 33
+    d.lut_enabled, d.lut, d.lut_size = 1, lut_dev.data.data_ptr(), 33
     d.lut_dmin, d.lut_dspan = (ctypes.c_float * 3)(0, 0, 0), (ctypes.c_float * 3)(1, 1, 1)
     d.lut_blend, d.lut_one_minus_blend = 1.0, 0.0
     d.stencil_op, d.stencil_strength, d.stencil_border = nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE

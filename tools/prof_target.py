@@ -20,7 +20,7 @@ dev = torch.device("cuda", 0)
 nv, ops = pkg._native, pkg.ops
 x = natural_frames(frames, 1080, 1920, seed=1, dtype=dt, device=dev) if dist == "nat" else torch.rand(frames, 1080, 1920, 3, device=dev).to(dt)
 lut = pkg.VRGDG_LUTS._parse_cube_file(os.path.join(LUTS, "B200 Vintage 33.cube"))
-lut_dev = lut["lut"].to(dev)
+lut_dev = ops.pack_lut(lut["lut"], dev)
 out = torch.empty_like(x)
 if what == "chain":
     chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), lut=dict(lut_data=lut, strength=10.0),

@@ -41,7 +41,7 @@ def report(name, ms, npix, bpp):
 
 def main():
     lut = pkg.VRGDG_LUTS._parse_cube_file(os.path.join(LUTS, "B200 Vintage 33.cube"))
-    lut_dev = lut["lut"].to(dev)
+    lut_dev = ops.pack_lut(lut["lut"], dev)
     for (B, H, W, dt, tag) in ((16, 1080, 1920, torch.float16, "1080p_f16"), (4, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float32, "1080p_f32")):
         for dist in ("nat", "white"):
             x = natural_frames(B, H, W, seed=1, dtype=dt, device=dev) if dist == "nat" else torch.rand(B, H, W, 3, device=dev).to(dt)
