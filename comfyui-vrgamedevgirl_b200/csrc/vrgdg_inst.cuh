@@ -68,7 +68,7 @@ cudaError_t launch_lut_rgba(const void* in, void* out, int64_t npix, const LutPa
 // ---- k_tile ------------------------------------------------------------------------------------
 template <typename T>
 void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y) {
-  using C = TileCfg<T, false>;     // tile geometry is the same for both thread configurations
+  using C = TileCfg<T, 0>;         // tile geometry is the same for every configuration
   tiles_x = (RW + C::TXE - 1) / C::TXE;
   tiles_y = (H + C::TY - 1) / C::TY;
   box_x = C::BX;
@@ -82,7 +82,7 @@ static cudaError_t launch_tile_k(const CUtensorMap* tmap, const void* in, void* 
   // per device context, so set on every launch (single-process multi-GPU hosts)
   cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return attr;
-  constexpr int NT = TileCfg<T, (MASK != 0)>::THREADS;
+  constexpr int NT = TileCfg<T, MASK>::THREADS;
   if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024)) + 1);
   static int occ = occupancy_of(kern, NT, smem);
   if (Q.total_tiles == 0) return cudaSuccess;

@@ -247,12 +247,16 @@ struct TileParams {
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
 };
 
-// HEAVY = per-pixel pre-stages enabled: one 512-thread CTA per SM with a 2-stage ring keeps ~150 KB of the SM's
-// 228 KB as L1 for the LUT gather; the pure stencils use 256-thread CTAs, a 3-stage ring and 2 CTAs per SM.
-template <typename T, bool HEAVY> struct TileCfg {
-  static constexpr int VEC = 16 / sizeof(T);          // output elements per thread per row
+// HEAVY = the LUT gather runs in the pre-stage: one 512-thread CTA per SM with a 2-stage ring leaves ~126 KB of the
+// SM's 228 KB as L1 for the table; everything else uses 256-thread CTAs, a 3-stage ring and 2 CTAs per SM.
+// WORK = 16-bit frames with pre-stages: their fp32 results live in a separate work tile, and a thread then produces
+// 4 elements per row (16-byte shared loads at a 16-byte lane stride are bank-conflict free; 32-byte strides are not).
+template <typename T, int MASK> struct TileCfg {
+  static constexpr bool HEAVY = (MASK & ST_LUT) != 0;
+  static constexpr bool WORK = (MASK != 0) && (sizeof(T) != 4);
+  static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
-  static constexpr int PADL = VEC;                    // box starts PADL elements left of the tile (>= 3)
+  static constexpr int PADL = 16 / (int)sizeof(T);    // box starts PADL elements left of the tile (>= 3, keeps 16-byte alignment)
   static constexpr int TXE = 240;                     // output elements per tile row (multiple of 6 and of VEC)
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
@@ -271,9 +275,9 @@ template <typename T, bool HEAVY> struct TileCfg {
 
 template <typename T, int MASK>
 constexpr size_t tile_smem_bytes() {
-  using C = TileCfg<T, (MASK != 0)>;
+  using C = TileCfg<T, MASK>;
   size_t s = (size_t)C::NS * C::STAGE_BYTES;
-  if (MASK != 0 && sizeof(T) != 4) s += (size_t)C::ROWS * C::BX * 4;   // fp32 work tile
+  if (C::WORK) s += (size_t)C::ROWS * C::BX * 4;      // fp32 work tile
   return s + 64 /* mbarriers */ + 128 /* alignment slack */;
 }
 
@@ -358,10 +362,17 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
   if (y < Q.H && ge0 < Q.RW) {
     T* dst = out + ((int64_t)frame * Q.H + y) * Q.RW + ge0;
     if (Q.vec_store) {
-      union { uint4 q; T e[VEC]; } u;
+      if (VEC * sizeof(T) == 16) {
+        union { uint4 q; T e[VEC]; } u;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
-      *reinterpret_cast<uint4*>(dst) = u.q;
+        for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
+        *reinterpret_cast<uint4*>(dst) = u.q;
+      } else {
+        union { uint2 q; T e[VEC]; } u;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
+        *reinterpret_cast<uint2*>(dst) = u.q;
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) if (ge0 + e < Q.RW) dst[e] = Elem<T>::st(o[e]);
@@ -369,10 +380,11 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
   }
 }
 
-template <typename T, int OP, bool WORK, bool HEAVY>
+template <typename T, int OP, int MASK>
 __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
                                              int frame, int y0, int x0e) {
-  using C = TileCfg<T, HEAVY>;
+  using C = TileCfg<T, MASK>;
+  constexpr bool WORK = C::WORK;
   constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, WN = VEC + 6;
   const int tid = threadIdx.x;
   if (tid >= C::COLS * C::RG) return;
@@ -432,15 +444,37 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
   }
 }
 
+// six consecutive staged elements (even element offset) as three 2-element words
+template <typename T>
+__device__ __forceinline__ void pair_load6(const T* p, bool word0, float* e) {
+  if (sizeof(T) == 4) {
+    const float2* q = reinterpret_cast<const float2*>(p);
+    if (word0) { float2 v = q[0]; e[0] = v.x; e[1] = v.y; }
+    float2 v1 = q[1], v2 = q[2];
+    e[2] = v1.x; e[3] = v1.y; e[4] = v2.x; e[5] = v2.y;
+  } else {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    union { uint32_t u[3]; T h[6]; } w;
+    w.u[0] = word0 ? q[0] : 0u; w.u[1] = q[1]; w.u[2] = q[2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e[i] = Elem<T>::ld(w.h[i]);
+  }
+}
+__device__ __forceinline__ void pair_store6(float* p, bool word0, const float* e) {
+  float2* q = reinterpret_cast<float2*>(p);
+  if (word0) q[0] = make_float2(e[0], e[1]);
+  q[1] = make_float2(e[2], e[3]);
+  q[2] = make_float2(e[4], e[5]);
+}
+
 template <typename T, int MASK, bool EXACT>
-__global__ void __launch_bounds__((TileCfg<T, (MASK != 0)>::THREADS), (TileCfg<T, (MASK != 0)>::MINB))
+__global__ void __launch_bounds__((TileCfg<T, MASK>::THREADS), (TileCfg<T, MASK>::MINB))
 k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __restrict__ out, TileParams Q) {
-  constexpr bool HEAVY = (MASK != 0);
-  using C = TileCfg<T, HEAVY>;
+  using C = TileCfg<T, MASK>;
   constexpr int NT = C::THREADS;
   constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, TXE = C::TXE, TY = C::TY, ROWS = C::ROWS;
   constexpr int NS = C::NS;
-  constexpr bool WORK = (MASK != 0) && (sizeof(T) != 4);   // separate fp32 tile for the pre-stage results
+  constexpr bool WORK = C::WORK;                           // separate fp32 tile for the pre-stage results
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -525,8 +559,11 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
         const bool need_a = (kx > 0), need_b = (kx < C::PAIRS - 1);
         const bool in_a = need_a && rowin && pxa >= 0 && pxa < Q.W;
         const bool in_b = need_b && rowin && pxa + 1 >= 0 && pxa + 1 < Q.W;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        // staged elements so..so+5 (pixel a = so..so+2, pixel b = so+3..so+5) move as three 2-element words: lane stride is
+        // 6 elements, so 32/64-bit shared accesses are bank-conflict free.  Word 0 lies left of the box when kx == 0.
+        float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (in_a | in_b) {
+          pair_load6<T>(raw + so, kx > 0, e);
           float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (GRAIN) {
             if (has_ext) {
@@ -537,22 +574,15 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
               grain_pair_normals(grain_pair_bits(P.gkey, gf, (uint32_t)pair, (uint32_t)y), z);
             }
           }
-          if (in_a) {
-            a0 = Elem<T>::ld(raw[so]); a1 = Elem<T>::ld(raw[so + 1]); a2 = Elem<T>::ld(raw[so + 2]);
-            process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], a0, a1, a2);
-          }
-          if (in_b) {
-            b0 = Elem<T>::ld(raw[so + 3]); b1 = Elem<T>::ld(raw[so + 4]); b2 = Elem<T>::ld(raw[so + 5]);
-            process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], b0, b1, b2);
-          }
+          if (in_a) process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], e[0], e[1], e[2]);
+          else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
+          if (in_b) process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], e[3], e[4], e[5]);
+          else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
         if (WORK) {
-          if (need_a) { work[so] = a0; work[so + 1] = a1; work[so + 2] = a2; }
-          if (need_b) { work[so + 3] = b0; work[so + 4] = b1; work[so + 5] = b2; }
-        } else {
-          float* rf = reinterpret_cast<float*>(raw);
-          if (in_a) { rf[so] = a0; rf[so + 1] = a1; rf[so + 2] = a2; }
-          if (in_b) { rf[so + 3] = b0; rf[so + 4] = b1; rf[so + 5] = b2; }
+          pair_store6(work + so, kx > 0, e);                       // zeros for pixels outside the image
+        } else if (in_a | in_b) {
+          pair_store6(reinterpret_cast<float*>(raw) + so, kx > 0, e);   // in place; untouched pixels keep their staged value
         }
       }
       __syncthreads();
@@ -567,12 +597,12 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     {
       const float* wt = WORK ? work : nullptr;
       switch (Q.op) {   // uniform; one specialised row loop per epilogue
-        case 1: stencil_rows<T, 1, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 2: stencil_rows<T, 2, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 3: stencil_rows<T, 3, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 4: stencil_rows<T, 4, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 5: stencil_rows<T, 5, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
-        default: stencil_rows<T, 0, WORK, HEAVY>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 1: stencil_rows<T, 1, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 2: stencil_rows<T, 2, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 3: stencil_rows<T, 3, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 4: stencil_rows<T, 4, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+        case 5: stencil_rows<T, 5, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+        default: stencil_rows<T, 0, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
       }
     }
     if (tma) fence_proxy_async();   // generic-proxy writes to this stage happen-before its next async refill

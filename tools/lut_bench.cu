@@ -29,7 +29,8 @@ template <bool DIV> __device__ __forceinline__ void coord(float v, float smax, i
 }
 
 // ---- variant A/B: [S^3][3] scalar loads --------------------------------------------------------
-template <bool EXACT, bool DIV>
+#define LDV(p) (SMEM ? *(p) : __ldg(p))
+template <bool EXACT, bool DIV, bool SMEM = false>
 __device__ __forceinline__ void eval_scalar(const float* __restrict__ L, int S, float& r, float& g, float& b) {
   Idx q; float smax = (float)(S - 1);
   coord<DIV>(r, smax, S, q.r0, q.r1, q.fr); coord<DIV>(g, smax, S, q.g0, q.g1, q.fg); coord<DIV>(b, smax, S, q.b0, q.b1, q.fb);
@@ -40,8 +41,8 @@ __device__ __forceinline__ void eval_scalar(const float* __restrict__ L, int S, 
   float omb = 1.f - q.fb, omg = 1.f - q.fg, omr = 1.f - q.fr, o[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float c00 = lerp1<EXACT>(__ldg(p000 + c), __ldg(p001 + c), q.fb, omb), c01 = lerp1<EXACT>(__ldg(p010 + c), __ldg(p011 + c), q.fb, omb);
-    float c10 = lerp1<EXACT>(__ldg(p100 + c), __ldg(p101 + c), q.fb, omb), c11 = lerp1<EXACT>(__ldg(p110 + c), __ldg(p111 + c), q.fb, omb);
+    float c00 = lerp1<EXACT>(LDV(p000 + c), LDV(p001 + c), q.fb, omb), c01 = lerp1<EXACT>(LDV(p010 + c), LDV(p011 + c), q.fb, omb);
+    float c10 = lerp1<EXACT>(LDV(p100 + c), LDV(p101 + c), q.fb, omb), c11 = lerp1<EXACT>(LDV(p110 + c), LDV(p111 + c), q.fb, omb);
     o[c] = clamp01(lerp1<EXACT>(lerp1<EXACT>(c00, c01, q.fg, omg), lerp1<EXACT>(c10, c11, q.fg, omg), q.fr, omr));
   }
   r = o[0]; g = o[1]; b = o[2];
@@ -89,6 +90,26 @@ __device__ __forceinline__ void eval_pair(const float* __restrict__ P, int S, fl
   r = o0; g = o1; b = o2;
 }
 
+// ---- variant 10: cell-packed [S^3] x 24 floats (8 corners x rgb) = 96 B, three 256-bit loads ----------------
+template <bool EXACT>
+__device__ __forceinline__ void eval_cell(const float* __restrict__ C, int S, float& r, float& g, float& b) {
+  Idx q; float smax = (float)(S - 1);
+  coord<false>(r, smax, S, q.r0, q.r1, q.fr); coord<false>(g, smax, S, q.g0, q.g1, q.fg); coord<false>(b, smax, S, q.b0, q.b1, q.fb);
+  const float* p = C + (size_t)((q.b0 * S + q.g0) * S + q.r0) * 24;
+  F8 a = ld256(p), c = ld256(p + 8), d = ld256(p + 16);
+  // order: c000 c100 c010 c110 c001 c101 c011 c111, 3 floats each
+  float v[24] = {a.a.x, a.a.y, a.a.z, a.a.w, a.b.x, a.b.y, a.b.z, a.b.w, c.a.x, c.a.y, c.a.z, c.a.w, c.b.x, c.b.y, c.b.z, c.b.w,
+                 d.a.x, d.a.y, d.a.z, d.a.w, d.b.x, d.b.y, d.b.z, d.b.w};
+  float omb = 1.f - q.fb, omg = 1.f - q.fg, omr = 1.f - q.fr, o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float c00 = lerp1<EXACT>(v[0 + ch], v[12 + ch], q.fb, omb), c10 = lerp1<EXACT>(v[3 + ch], v[15 + ch], q.fb, omb);
+    float c01 = lerp1<EXACT>(v[6 + ch], v[18 + ch], q.fb, omb), c11 = lerp1<EXACT>(v[9 + ch], v[21 + ch], q.fb, omb);
+    o[ch] = clamp01(lerp1<EXACT>(lerp1<EXACT>(c00, c01, q.fg, omg), lerp1<EXACT>(c10, c11, q.fg, omg), q.fr, omr));
+  }
+  r = o[0]; g = o[1]; b = o[2];
+}
+
 template <typename T> struct E;
 template <> struct E<float> { static __device__ float ld(float v) { return v; } static __device__ float st(float v) { return v; } };
 template <> struct E<__half> { static __device__ float ld(__half v) { return __half2float(v); } static __device__ __half st(float v) { return __float2half_rn(v); } };
@@ -97,7 +118,8 @@ template <> struct E<__half> { static __device__ float ld(__half v) { return __h
 //      7 smem scalar [S^3][3] exact, 8 smem f4 exact, 9 passthrough (I/O only)
 template <typename T, int VAR>
 __global__ void __launch_bounds__(256) k_lut(const T* __restrict__ in, T* __restrict__ out, int64_t npix, const float* __restrict__ lut3,
-                                              const float4* __restrict__ lut4, const float* __restrict__ lutp, int S) {
+                                              const float4* __restrict__ lut4, const float* __restrict__ lutp, int S,
+                                              const float* __restrict__ lutc = nullptr) {
   extern __shared__ float4 sm4[];
   float* sm = reinterpret_cast<float*>(sm4);
   if (VAR == 7) { for (int i = threadIdx.x; i < S * S * S * 3; i += 256) sm[i] = lut3[i]; __syncthreads(); }
@@ -118,7 +140,8 @@ __global__ void __launch_bounds__(256) k_lut(const T* __restrict__ in, T* __rest
       if (VAR == 4) eval_pair<true, false>(lutp, S, r, g, b);
       if (VAR == 5) eval_pair<true, true>(lutp, S, r, g, b);
       if (VAR == 6) eval_pair<false, true>(lutp, S, r, g, b);
-      if (VAR == 7) eval_scalar<true, false>(sm, S, r, g, b);
+      if (VAR == 7) eval_scalar<true, false, true>(sm, S, r, g, b);
+      if (VAR == 10) eval_cell<true>(lutc, S, r, g, b);
       if (VAR == 8) eval_f4<true>([&](int i) { return sm4[i]; }, S, r, g, b);
       u.e[3 * j] = E<T>::st(r); u.e[3 * j + 1] = E<T>::st(g); u.e[3 * j + 2] = E<T>::st(b);
     }
@@ -139,13 +162,18 @@ template <typename T> __global__ void k_fill(T* p, int64_t npix, int W, int H, i
       g = 0.5f + 0.25f * __sinf(x * 0.007f + 1.3f) + 0.2f * __sinf(y * 0.017f + 0.5f) + 0.02f * (n1 - 0.5f);
       b = 0.45f + 0.25f * __sinf(x * 0.005f + 2.1f) + 0.2f * __sinf(y * 0.009f + 1.5f) + 0.02f * (n2 - 0.5f);
     }
+    if (mode == 2) {   // natural + film-grain-like Gaussian noise (sigma 0.08 / 0.04 / 0.12): what the LUT sees after FastFilmGrain
+      float u1 = (n0 * 65535.f + 1.f) / 65537.f, rr = sqrtf(-2.f * __logf(u1));
+      float u2 = (n2 * 65535.f + 1.f) / 65537.f, r2 = sqrtf(-2.f * __logf(u2));
+      r += 0.08f * rr * __cosf(6.2831853f * n1); g += 0.04f * rr * __sinf(6.2831853f * n1); b += 0.12f * r2 * __cosf(6.2831853f * n0);
+    }
     p[i * 3] = E<T>::st(clamp01(r)); p[i * 3 + 1] = E<T>::st(clamp01(g)); p[i * 3 + 2] = E<T>::st(clamp01(b));
   }
 }
 
 template <typename T, int VAR>
 void run(const char* name, const char* tname, const T* in, T* out, int64_t npix, const float* l3, const float4* l4, const float* lp, int S,
-         size_t smem, int sms, const char* dist, const T* check) {
+         size_t smem, int sms, const char* dist, const T* check, const float* lc = nullptr) {
   auto kern = k_lut<T, VAR>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (smem == 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -153,11 +181,11 @@ void run(const char* name, const char* tname, const T* in, T* out, int64_t npix,
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
   int grid = sms * (occ > 0 ? occ : 1) * (smem ? 1 : 4);
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-  for (int i = 0; i < 2; ++i) kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S);
+  for (int i = 0; i < 2; ++i) kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc);
   CK(cudaDeviceSynchronize());
   float best = 1e9f;
   for (int i = 0; i < 5; ++i) {
-    CK(cudaEventRecord(a)); kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    CK(cudaEventRecord(a)); kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
     float ms; CK(cudaEventElapsedTime(&ms, a, b)); best = fminf(best, ms);
   }
   // max diff vs the reference variant's output (first 1M elements)
@@ -179,7 +207,7 @@ template <typename T> void suite(const char* tname, int sms) {
   const int64_t npix = (int64_t)B * W * H;
   T *in, *out, *ref;
   CK(cudaMalloc(&in, npix * 3 * sizeof(T))); CK(cudaMalloc(&out, npix * 3 * sizeof(T))); CK(cudaMalloc(&ref, npix * 3 * sizeof(T)));
-  for (int S : {33, 17, 65}) {
+  for (int S : {33, 17}) {
     size_t n = (size_t)S * S * S;
     std::vector<float> h3(n * 3), hp(n * 8, 0.f); std::vector<float4> h4(n);
     for (int b = 0; b < S; ++b) for (int g = 0; g < S; ++g) for (int r = 0; r < S; ++r) {
@@ -194,12 +222,20 @@ template <typename T> void suite(const char* tname, int sms) {
       size_t i = ((size_t)b * S + g) * S + r, i1 = ((size_t)b * S + g) * S + (r + 1 < S ? r + 1 : S - 1);
       for (int c = 0; c < 3; ++c) { hp[i * 8 + c] = h3[i * 3 + c]; hp[i * 8 + 4 + c] = h3[i1 * 3 + c]; }
     }
-    float *l3, *lp; float4* l4;
-    CK(cudaMalloc(&l3, n * 12)); CK(cudaMalloc(&l4, n * 16)); CK(cudaMalloc(&lp, n * 32));
+    std::vector<float> hc(n * 24, 0.f);
+    for (int b = 0; b < S; ++b) for (int g = 0; g < S; ++g) for (int r = 0; r < S; ++r) {
+      size_t i = ((size_t)b * S + g) * S + r;
+      int b1 = b + 1 < S ? b + 1 : S - 1, g1 = g + 1 < S ? g + 1 : S - 1, r1 = r + 1 < S ? r + 1 : S - 1;
+      int cb[8] = {b, b, b, b, b1, b1, b1, b1}, cg[8] = {g, g, g1, g1, g, g, g1, g1}, cr[8] = {r, r1, r, r1, r, r1, r, r1};
+      for (int k = 0; k < 8; ++k) for (int c = 0; c < 3; ++c) hc[i * 24 + k * 3 + c] = h3[(((size_t)cb[k] * S + cg[k]) * S + cr[k]) * 3 + c];
+    }
+    float *l3, *lp, *lc; float4* l4;
+    CK(cudaMalloc(&l3, n * 12)); CK(cudaMalloc(&l4, n * 16)); CK(cudaMalloc(&lp, n * 32)); CK(cudaMalloc(&lc, n * 96));
+    CK(cudaMemcpy(lc, hc.data(), n * 96, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(l3, h3.data(), n * 12, cudaMemcpyHostToDevice)); CK(cudaMemcpy(l4, h4.data(), n * 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(lp, hp.data(), n * 32, cudaMemcpyHostToDevice));
-    for (int mode = 1; mode >= 0; --mode) {
-      const char* dist = mode ? "natural" : "white";
+    for (int mode = 2; mode >= 0; --mode) {
+      const char* dist = mode == 2 ? "natural+grain" : (mode ? "natural" : "white");
       k_fill<T><<<sms * 8, 256>>>(in, npix, W, H, mode, 12345u);
       CK(cudaDeviceSynchronize());
       if (S == 33 && mode == 1) run<T, 9>("io_only", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, nullptr);
@@ -210,10 +246,11 @@ template <typename T> void suite(const char* tname, int sms) {
       run<T, 4>("v4_pair_2x128_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
       run<T, 5>("v5_pair_256_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
       run<T, 6>("v6_pair_256_fast", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
+      run<T, 10>("v10_cell_3x256_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc);
       if (n * 12 <= 200 * 1024) run<T, 7>("v7_smem_scalar_exact", tname, in, out, npix, l3, l4, lp, S, n * 12, sms, dist, ref);
       if (n * 16 <= 200 * 1024) run<T, 8>("v8_smem_f4_exact", tname, in, out, npix, l3, l4, lp, S, n * 16, sms, dist, ref);
     }
-    cudaFree(l3); cudaFree(l4); cudaFree(lp);
+    cudaFree(l3); cudaFree(l4); cudaFree(lp); cudaFree(lc);
   }
   cudaFree(in); cudaFree(out); cudaFree(ref);
 }
