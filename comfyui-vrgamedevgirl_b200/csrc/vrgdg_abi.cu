@@ -165,7 +165,7 @@ int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int64_t vrgdg_lut3d_packed_bytes(int lut_size) {
   if (lut_size < 2 || lut_size > 256) return 0;
-  return (int64_t)lut_size * lut_size * lut_size * 8 * (int64_t)sizeof(float);
+  return (int64_t)lut_size * lut_size * lut_size * LUT_CELL_FLOATS * (int64_t)sizeof(float);
 }
 
 int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream) {

@@ -707,17 +707,17 @@ static __global__ void k_colormatch_params(const double* __restrict__ fs, int B,
   }
 }
 
-// reference-layout table [S][S][S][3] -> pair table (see vrgdg_math.cuh)
+// reference-layout table [S][S][S][3] -> cell table (see vrgdg_math.cuh)
 static __global__ void __launch_bounds__(256)
 k_lut_pack(const float* __restrict__ lut3, float* __restrict__ packed, int S) {
   const int n = S * S * S;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const int r = i % S, g = (i / S) % S, b = i / (S * S);
-    float e[8];
+    float e[LUT_CELL_FLOATS];
     lut_pack_entry(lut3, S, b, g, r, e);
-    float4* d = reinterpret_cast<float4*>(packed + (size_t)i * 8);
-    d[0] = make_float4(e[0], e[1], e[2], e[3]);
-    d[1] = make_float4(e[4], e[5], e[6], e[7]);
+    float4* d = reinterpret_cast<float4*>(packed + (size_t)i * LUT_CELL_FLOATS);
+#pragma unroll
+    for (int k = 0; k < LUT_CELL_FLOATS / 4; ++k) d[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
   }
 }
 

@@ -199,12 +199,13 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 }
 
 // ---- 3D LUT trilinear: VRGDG_IV_Adjustments.py:293-336 ------------------------------------------
-// Device table layout ("pair table", built by lut_pack_entry / vrgdg_lut3d_pack):
-//   entry (b,g,r) = { lut[b,g,r,0..2], 0, lut[b,g,min(r+1,S-1),0..2], 0 }   32 bytes, 32-byte aligned
-// so the two red neighbours of a cell edge arrive with ONE 256-bit load (LDG.E.256) and a pixel needs 4 loads
-// instead of 24.  The gather is bound by L1 tag lookups per divergent lane (see profiles/), not by bytes.
+// Device table layout ("cell table", built by lut_pack_entry / vrgdg_lut3d_pack): one 96-byte entry per cell origin
+//   entry (b,g,r) = { c000 c100 c010 c110 c001 c101 c011 c111 } x rgb,  cXYZ = lut[min(b+Z,S-1), min(g+Y,S-1), min(r+X,S-1), :]
+// so a pixel fetches its 8 corners (24 floats) with THREE 256-bit loads (LDG.E.256) from consecutive addresses instead of
+// 24 scalar loads.  The gather is bound by L1 tag lookups per divergent lane, not by bytes (profiles/: 4 lookups/px with a
+// 32-byte r-pair table = 60-65 Gpx/s on grained frames, 3 lookups/px with this layout = 73-84 Gpx/s, 24 scalar = 34).
 struct LutParams {
-  const float* lut;      // pair table, S*S*S*8 floats
+  const float* lut;      // cell table, S*S*S*24 floats
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -212,9 +213,11 @@ struct LutParams {
   int unit_domain;       // dmin == 0 and dspan == 1: (x-0)/1 == x exactly, the division is skipped
 };
 
+constexpr int LUT_CELL_FLOATS = 24;
+
 struct F8 { float v[8]; };
 
-VRGDG_HD F8 lut_load_pair(const float* p) {
+VRGDG_HD F8 lut_load8(const float* p) {
   F8 q;
 #if defined(__CUDA_ARCH__)
   asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -226,13 +229,17 @@ VRGDG_HD F8 lut_load_pair(const float* p) {
   return q;
 }
 
-// one pair-table entry from the reference-layout table [S][S][S][3]
-VRGDG_HD void lut_pack_entry(const float* lut3, int S, int b, int g, int r, float* dst8) {
-  const int r1 = (r + 1 < S) ? r + 1 : S - 1;
-  const float* a = lut3 + ((size_t)(b * S + g) * S + r) * 3;
-  const float* c = lut3 + ((size_t)(b * S + g) * S + r1) * 3;
-  dst8[0] = a[0]; dst8[1] = a[1]; dst8[2] = a[2]; dst8[3] = 0.0f;
-  dst8[4] = c[0]; dst8[5] = c[1]; dst8[6] = c[2]; dst8[7] = 0.0f;
+// one cell-table entry from the reference-layout table [S][S][S][3]
+VRGDG_HD void lut_pack_entry(const float* lut3, int S, int b, int g, int r, float* dst24) {
+  const int b1 = (b + 1 < S) ? b + 1 : S - 1, g1 = (g + 1 < S) ? g + 1 : S - 1, r1 = (r + 1 < S) ? r + 1 : S - 1;
+  const int cb[8] = {b, b, b, b, b1, b1, b1, b1};
+  const int cg[8] = {g, g, g1, g1, g, g, g1, g1};
+  const int cr[8] = {r, r1, r, r1, r, r1, r, r1};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* a = lut3 + ((size_t)(cb[k] * S + cg[k]) * S + cr[k]) * 3;
+    dst24[3 * k] = a[0]; dst24[3 * k + 1] = a[1]; dst24[3 * k + 2] = a[2];
+  }
 }
 
 // coordinate -> (cell index, fraction); bit-exact with :296-316
@@ -259,22 +266,21 @@ VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
   lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
   lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
-  (void)r1;                                         // the red neighbour is the second half of the pair entry
-  const int S = P.S;
-  const float* L = P.lut;
-  // pair entries of the four (b,g) edges at r0:  v[0..2] = lut[b,g,r0], v[4..6] = lut[b,g,r1]
-  const F8 e00 = lut_load_pair(L + (size_t)((b0 * S + g0) * S + r0) * 8);   // c000 | c100
-  const F8 e01 = lut_load_pair(L + (size_t)((b1 * S + g0) * S + r0) * 8);   // c001 | c101
-  const F8 e10 = lut_load_pair(L + (size_t)((b0 * S + g1) * S + r0) * 8);   // c010 | c110
-  const F8 e11 = lut_load_pair(L + (size_t)((b1 * S + g1) * S + r0) * 8);   // c011 | c111
+  (void)r1; (void)g1; (void)b1;                     // the clamped neighbours are baked into the cell entry
+  const float* p = P.lut + (size_t)((b0 * P.S + g0) * P.S + r0) * LUT_CELL_FLOATS;
+  const F8 q0 = lut_load8(p), q1 = lut_load8(p + 8), q2 = lut_load8(p + 16);
+  // v[3k+ch]: k = 0..7 -> c000 c100 c010 c110 c001 c101 c011 c111
+  const float v[24] = {q0.v[0], q0.v[1], q0.v[2], q0.v[3], q0.v[4], q0.v[5], q0.v[6], q0.v[7],
+                       q1.v[0], q1.v[1], q1.v[2], q1.v[3], q1.v[4], q1.v[5], q1.v[6], q1.v[7],
+                       q2.v[0], q2.v[1], q2.v[2], q2.v[3], q2.v[4], q2.v[5], q2.v[6], q2.v[7]};
   const float omb = subx(1.0f, fb), omg = subx(1.0f, fg), omr = subx(1.0f, fr);
   float o[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    float c00 = lerp_ref<EXACT>(e00.v[ch], e01.v[ch], fb, omb);           // c000*(1-fb) + c001*fb
-    float c01 = lerp_ref<EXACT>(e10.v[ch], e11.v[ch], fb, omb);           // c010, c011
-    float c10 = lerp_ref<EXACT>(e00.v[4 + ch], e01.v[4 + ch], fb, omb);   // c100, c101
-    float c11 = lerp_ref<EXACT>(e10.v[4 + ch], e11.v[4 + ch], fb, omb);   // c110, c111
+    float c00 = lerp_ref<EXACT>(v[0 + ch], v[12 + ch], fb, omb);     // c000*(1-fb) + c001*fb
+    float c01 = lerp_ref<EXACT>(v[6 + ch], v[18 + ch], fb, omb);     // c010, c011
+    float c10 = lerp_ref<EXACT>(v[3 + ch], v[15 + ch], fb, omb);     // c100, c101
+    float c11 = lerp_ref<EXACT>(v[9 + ch], v[21 + ch], fb, omb);     // c110, c111
     float c0 = lerp_ref<EXACT>(c00, c01, fg, omg);
     float c1 = lerp_ref<EXACT>(c10, c11, fg, omg);
     o[ch] = clamp01(lerp_ref<EXACT>(c0, c1, fr, omr));

@@ -19,7 +19,7 @@ def _f32(v):
 
 
 class PackedLut:
-    """A 3D LUT in the library's device layout (vrgdg_lut3d_pack): `data` float32 [S^3 * 8] on a CUDA device."""
+    """A 3D LUT in the library's device layout (vrgdg_lut3d_pack): `data` float32 [S^3 * 24] on a CUDA device."""
 
     def __init__(self, data, size):
         self.data, self.size = data, int(size)

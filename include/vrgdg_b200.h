@@ -87,7 +87,8 @@ VRGDG_API const char* vrgdg_last_tile_path(void);
  * Output is bit-identical to the reference CPU path for fp32 frames. */
 VRGDG_API int64_t vrgdg_lut3d_packed_bytes(int lut_size);
 /* lut: device [S,S,S,3] fp32 (reference layout); packed: device buffer of vrgdg_lut3d_packed_bytes(S), 32-byte aligned.
- * Entry (b,g,r) of the packed table = {lut[b,g,r,:], 0, lut[b,g,min(r+1,S-1),:], 0}: one 256-bit load per cell edge. */
+ * Entry (b,g,r) of the packed table = the 8 corners of the cell whose origin is (b,g,r) (neighbours clamped to S-1), 24 floats
+ * = 96 bytes: a pixel's whole trilinear stencil arrives with three consecutive 256-bit loads. */
 VRGDG_API int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream);
 VRGDG_API int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype,
                       const float* lut_packed, int lut_size,

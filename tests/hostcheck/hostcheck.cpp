@@ -50,9 +50,9 @@ void hc_grain(const float* in, const float* noise, float* out, int64_t n, float 
 void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, const float* dmin, const float* dspan,
               float blend, float omb, int exact) {
   // same packing as vrgdg_lut3d_pack
-  float* packed = new float[(size_t)S * S * S * 8];
+  float* packed = new float[(size_t)S * S * S * LUT_CELL_FLOATS];
   for (int bb = 0; bb < S; ++bb) for (int gg = 0; gg < S; ++gg) for (int rr = 0; rr < S; ++rr)
-    lut_pack_entry(lut, S, bb, gg, rr, packed + ((size_t)(bb * S + gg) * S + rr) * 8);
+    lut_pack_entry(lut, S, bb, gg, rr, packed + ((size_t)(bb * S + gg) * S + rr) * LUT_CELL_FLOATS);
   LutParams P;
   P.lut = packed; P.S = S; P.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }

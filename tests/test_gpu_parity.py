@@ -418,3 +418,53 @@ def test_error_mapping(pkg, cuda_device):
     # empty batch is a no-op
     e = pkg.ops.grain(torch.zeros(0, 4, 4, 3, device=cuda_device), 0.1, 0.5, 0.5, seed=1)
     assert e.shape == (0, 4, 4, 3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# full-size, size-independent properties for the colour-match configs (configs[2], configs[3])
+# ------------------------------------------------------------------------------------------------------
+def test_colormatch_full_size_self_reference_is_identity(pkg, cuda_device):
+    """4K frames matched to THEMSELVES (each frame its own reference, batch-wise reference) must come back unchanged:
+    (lab-mu)/sd*sd+mu == lab up to rounding, then Lab->RGB inverts RGB->Lab.  Exercises moments + params + apply at 4K."""
+    x = natural_frames(2, 2160, 3840, seed=31, device=cuda_device)
+    x[1] = (x[1] * 0.6 + 0.2)
+    out = pkg.ColorMatchToReference().match_color(x, x, 1.0, 2)[0]
+    assert out.device.type == "cuda" and maxdiff(out, x) <= 2e-5     # Lab round trip in fp32 (oracle: 2e-5 on the same test)
+    half = pkg.ColorMatchToReference().match_color(x, x[:1].contiguous(), 0.0, 1)[0]   # strength 0: pure Lab round trip
+    assert maxdiff(half, x) <= 2e-5
+
+
+def test_colormatch_moves_statistics_onto_the_reference(pkg, cuda_device, oracle):
+    """after a full-strength match the frame's LAB mean/std equal the reference's (what the node is for), at 1080p"""
+    x = natural_frames(2, 1080, 1920, seed=32, device=cuda_device)
+    ref = (natural_frames(1, 720, 1280, seed=33, device=cuda_device) * torch.tensor([0.9, 0.7, 0.8], device=cuda_device) + 0.05).clamp(0, 1)
+    out = pkg.ColorMatchToReference().match_color(x, ref, 1.0, 1)[0]
+    def stats(t):
+        s = pkg.ops.lab_moments(t).cpu()
+        n, m = s[:, :1], s[:, 1:4] / s[:, :1]
+        return m, ((s[:, 4:7] - s[:, 1:4] * m) / (n - 1)).sqrt()
+    mo, so = stats(out)
+    mr, sr = stats(ref)
+    inside = float(((out > 0) & (out < 1)).float().mean())
+    assert inside > 0.98                                  # little clipping, otherwise the statistics cannot match
+    assert float((mo - mr).abs().max()) < 0.5 and float((so / sr - 1).abs().max()) < 0.03
+
+
+def test_full_chain_with_colormatch_partition_invariance(pkg, cuda_device):
+    """configs[3] shape property: grain -> colour match -> LUT -> unsharp on shards == on the whole clip (frame-sharded dp)."""
+    nv = pkg._native
+    x = natural_frames(4, 270, 480, seed=34, device=cuda_device)
+    ref = natural_frames(1, 135, 240, seed=35, device=cuda_device)
+    lut = _lut33(pkg)
+    mk = lambda: pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(reference_image=ref, strength=1.0),
+                                     lut=dict(lut_data=lut, strength=10.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    whole = mk()(x, first_frame=0)
+    parts = torch.cat([mk()(x[:1].contiguous(), first_frame=0), mk()(x[1:].contiguous(), first_frame=1)])
+    assert torch.equal(whole, parts)
+    # and equals the unfused sequence of kernels
+    a = pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=42)
+    params = pkg.ops.colormatch_params(pkg.ops.lab_moments(a), pkg.ops.lab_moments(ref))
+    b = pkg.ops.colormatch_apply(a, params, 1.0, 0.0)
+    c = pkg.ops.lut3d_apply(b, lut["lut"], [0, 0, 0], [1, 1, 1], 1.0, 0.0)
+    d = pkg.ops.stencil3x3(c, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
+    assert maxdiff(whole, d) <= 5e-6

@@ -110,6 +110,36 @@ __device__ __forceinline__ void eval_cell(const float* __restrict__ C, int S, fl
   r = o[0]; g = o[1]; b = o[2];
 }
 
+// ---- variant 11: cell-packed unorm21: 8 corners x 8 B = 64 B, two 256-bit loads; values must lie in [0,1] --------
+__device__ __forceinline__ void dec21(uint32_t w0, uint32_t w1, float& r, float& g, float& b) {
+  const uint32_t M = 0x1FFFFFu, C = 0x4B000000u;                  // float(k) = as_float(C | k) - 2^23 for k < 2^23
+  r = __uint_as_float((w0 & M) | C) - 8388608.0f;
+  g = __uint_as_float((__funnelshift_r(w0, w1, 21) & M) | C) - 8388608.0f;
+  b = __uint_as_float(((w1 >> 10) & M) | C) - 8388608.0f;
+}
+__device__ __forceinline__ void eval_cell21(const float* __restrict__ Cq, int S, float& r, float& g, float& b) {
+  Idx q; float smax = (float)(S - 1);
+  coord<false>(r, smax, S, q.r0, q.r1, q.fr); coord<false>(g, smax, S, q.g0, q.g1, q.fg); coord<false>(b, smax, S, q.b0, q.b1, q.fb);
+  const float* p = Cq + (size_t)((q.b0 * S + q.g0) * S + q.r0) * 16;
+  F8 lo = ld256(p), hi = ld256(p + 8);
+  uint32_t w[16] = {__float_as_uint(lo.a.x), __float_as_uint(lo.a.y), __float_as_uint(lo.a.z), __float_as_uint(lo.a.w),
+                    __float_as_uint(lo.b.x), __float_as_uint(lo.b.y), __float_as_uint(lo.b.z), __float_as_uint(lo.b.w),
+                    __float_as_uint(hi.a.x), __float_as_uint(hi.a.y), __float_as_uint(hi.a.z), __float_as_uint(hi.a.w),
+                    __float_as_uint(hi.b.x), __float_as_uint(hi.b.y), __float_as_uint(hi.b.z), __float_as_uint(hi.b.w)};
+  float v[8][3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dec21(w[2 * k], w[2 * k + 1], v[k][0], v[k][1], v[k][2]);
+  float o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {       // corner order c000 c100 c010 c110 | c001 c101 c011 c111 (x=r, y=g, z=b)
+    float c00 = fmaf(q.fb, v[4][ch] - v[0][ch], v[0][ch]), c10 = fmaf(q.fb, v[5][ch] - v[1][ch], v[1][ch]);
+    float c01 = fmaf(q.fb, v[6][ch] - v[2][ch], v[2][ch]), c11 = fmaf(q.fb, v[7][ch] - v[3][ch], v[3][ch]);
+    float c0 = fmaf(q.fg, c01 - c00, c00), c1 = fmaf(q.fg, c11 - c10, c10);
+    o[ch] = clamp01(fmaf(q.fr, c1 - c0, c0) * 4.76837158203125e-07f);
+  }
+  r = o[0]; g = o[1]; b = o[2];
+}
+
 template <typename T> struct E;
 template <> struct E<float> { static __device__ float ld(float v) { return v; } static __device__ float st(float v) { return v; } };
 template <> struct E<__half> { static __device__ float ld(__half v) { return __half2float(v); } static __device__ __half st(float v) { return __float2half_rn(v); } };
@@ -119,7 +149,7 @@ template <> struct E<__half> { static __device__ float ld(__half v) { return __h
 template <typename T, int VAR>
 __global__ void __launch_bounds__(256) k_lut(const T* __restrict__ in, T* __restrict__ out, int64_t npix, const float* __restrict__ lut3,
                                               const float4* __restrict__ lut4, const float* __restrict__ lutp, int S,
-                                              const float* __restrict__ lutc = nullptr) {
+                                              const float* __restrict__ lutc = nullptr, const float* __restrict__ lutq = nullptr) {
   extern __shared__ float4 sm4[];
   float* sm = reinterpret_cast<float*>(sm4);
   if (VAR == 7) { for (int i = threadIdx.x; i < S * S * S * 3; i += 256) sm[i] = lut3[i]; __syncthreads(); }
@@ -142,6 +172,7 @@ __global__ void __launch_bounds__(256) k_lut(const T* __restrict__ in, T* __rest
       if (VAR == 6) eval_pair<false, true>(lutp, S, r, g, b);
       if (VAR == 7) eval_scalar<true, false, true>(sm, S, r, g, b);
       if (VAR == 10) eval_cell<true>(lutc, S, r, g, b);
+      if (VAR == 11) eval_cell21(lutq, S, r, g, b);
       if (VAR == 8) eval_f4<true>([&](int i) { return sm4[i]; }, S, r, g, b);
       u.e[3 * j] = E<T>::st(r); u.e[3 * j + 1] = E<T>::st(g); u.e[3 * j + 2] = E<T>::st(b);
     }
@@ -173,7 +204,7 @@ template <typename T> __global__ void k_fill(T* p, int64_t npix, int W, int H, i
 
 template <typename T, int VAR>
 void run(const char* name, const char* tname, const T* in, T* out, int64_t npix, const float* l3, const float4* l4, const float* lp, int S,
-         size_t smem, int sms, const char* dist, const T* check, const float* lc = nullptr) {
+         size_t smem, int sms, const char* dist, const T* check, const float* lc = nullptr, const float* lq = nullptr) {
   auto kern = k_lut<T, VAR>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (smem == 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
@@ -181,11 +212,11 @@ void run(const char* name, const char* tname, const T* in, T* out, int64_t npix,
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
   int grid = sms * (occ > 0 ? occ : 1) * (smem ? 1 : 4);
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-  for (int i = 0; i < 2; ++i) kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc);
+  for (int i = 0; i < 2; ++i) kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc, lq);
   CK(cudaDeviceSynchronize());
   float best = 1e9f;
   for (int i = 0; i < 5; ++i) {
-    CK(cudaEventRecord(a)); kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    CK(cudaEventRecord(a)); kern<<<grid, 256, smem>>>(in, out, npix, l3, l4, lp, S, lc, lq); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
     float ms; CK(cudaEventElapsedTime(&ms, a, b)); best = fminf(best, ms);
   }
   // max diff vs the reference variant's output (first 1M elements)
@@ -229,6 +260,14 @@ template <typename T> void suite(const char* tname, int sms) {
       int cb[8] = {b, b, b, b, b1, b1, b1, b1}, cg[8] = {g, g, g1, g1, g, g, g1, g1}, cr[8] = {r, r1, r, r1, r, r1, r, r1};
       for (int k = 0; k < 8; ++k) for (int c = 0; c < 3; ++c) hc[i * 24 + k * 3 + c] = h3[(((size_t)cb[k] * S + cg[k]) * S + cr[k]) * 3 + c];
     }
+    std::vector<uint32_t> hq(n * 16, 0u);
+    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 8; ++k) {
+      uint32_t q[3];
+      for (int c = 0; c < 3; ++c) q[c] = (uint32_t)llround((double)hc[i * 24 + k * 3 + c] * 2097151.0);   // unorm21 (scale 2^21-1 ~ 2^21)
+      hq[i * 16 + 2 * k] = q[0] | (q[1] << 21);
+      hq[i * 16 + 2 * k + 1] = (q[1] >> 11) | (q[2] << 10);
+    }
+    float* lq; CK(cudaMalloc(&lq, n * 64)); CK(cudaMemcpy(lq, hq.data(), n * 64, cudaMemcpyHostToDevice));
     float *l3, *lp, *lc; float4* l4;
     CK(cudaMalloc(&l3, n * 12)); CK(cudaMalloc(&l4, n * 16)); CK(cudaMalloc(&lp, n * 32)); CK(cudaMalloc(&lc, n * 96));
     CK(cudaMemcpy(lc, hc.data(), n * 96, cudaMemcpyHostToDevice));
@@ -247,10 +286,11 @@ template <typename T> void suite(const char* tname, int sms) {
       run<T, 5>("v5_pair_256_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
       run<T, 6>("v6_pair_256_fast", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
       run<T, 10>("v10_cell_3x256_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc);
+      run<T, 11>("v11_cell_u21_2x256", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc, lq);
       if (n * 12 <= 200 * 1024) run<T, 7>("v7_smem_scalar_exact", tname, in, out, npix, l3, l4, lp, S, n * 12, sms, dist, ref);
       if (n * 16 <= 200 * 1024) run<T, 8>("v8_smem_f4_exact", tname, in, out, npix, l3, l4, lp, S, n * 16, sms, dist, ref);
     }
-    cudaFree(l3); cudaFree(l4); cudaFree(lp); cudaFree(lc);
+    cudaFree(l3); cudaFree(l4); cudaFree(lp); cudaFree(lc); cudaFree(lq);
   }
   cudaFree(in); cudaFree(out); cudaFree(ref);
 }
