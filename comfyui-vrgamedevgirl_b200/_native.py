@@ -21,6 +21,7 @@ DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 STENCIL_NONE, STENCIL_BOX_UNSHARP, STENCIL_LAPLACIAN_CPU, STENCIL_LAPLACIAN_GPU, STENCIL_SOBEL_CPU, STENCIL_SOBEL_GPU = range(6)
 BORDER_REPLICATE, BORDER_ZERO = 0, 1
 SEED_PER_CLIP, SEED_PER_FRAME = 0, 1
+CHAIN_FAST_MATH = 1
 
 
 class ChainDesc(ctypes.Structure):
@@ -79,7 +80,7 @@ SIGNATURES = {
     "vrgdg_colormatch_params": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "vrgdg_colormatch_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _vp]),
     "vrgdg_chain_apply": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp]),
-    "vrgdg_chain_apply_ext": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp]),
+    "vrgdg_chain_apply_ext": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _i, _vp]),
     "vrgdg_chain_lab_moments": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp, _i64, _vp]),
     "vrgdg_u8bgr_to_rgb": (_i, [_vp, _vp, _i64, _i, _vp]),
     "vrgdg_rgb_to_u8bgr": (_i, [_vp, _vp, _i64, _i, _vp]),

@@ -84,11 +84,12 @@ class PostChain:
             d.cm_t, d.cm_one_minus_t = t, 1.0 - t
         return d
 
-    def __call__(self, frames, first_frame=0, ext_noise=None, out=None):
-        """frames: CUDA [B,H,W,3]; first_frame: absolute index of frames[0] in the clip (keys the grain)."""
+    def __call__(self, frames, first_frame=0, ext_noise=None, out=None, fast_math=False):
+        """frames: CUDA [B,H,W,3]; first_frame: absolute index of frames[0] in the clip (keys the grain).
+        ext_noise (tests): N(0,1) tensor replacing the generator; fast_math then selects the production arithmetic."""
         keep = []
         d = self._desc(frames, first_frame, keep)
-        return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out)
+        return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out, fast_math=fast_math)
 
     def run_host(self, frames_cpu, chunk_frames=8, first_frame=0, out=None):
         """Host frames in, host frames out: chunked upload / compute / download on three streams.  Pass pinned tensors

@@ -103,8 +103,15 @@ bool build_tmap(CUtensorMap* map, const void* in, int B, int H, int RW, int dtyp
   return r == CUDA_SUCCESS;
 }
 
+// packed LUT buffer = [fp32 cells: S^3*24 floats][unorm21 cells: S^3*16 words][bad-value count: 1 int, padded to 32 bytes]
+size_t lut_cells_floats(int S) { return (size_t)S * S * S * LUT_CELL_FLOATS; }
+size_t lut_q21_words(int S) { return (size_t)S * S * S * 16; }
+
 void fill_lut(LutParams& L, const float* lut, int S, const float* dmin, const float* dspan, float blend, float omb) {
   L.lut = lut; L.S = S; L.smax = (float)(S - 1);
+  L.q21 = reinterpret_cast<const uint32_t*>(lut + lut_cells_floats(S));
+  L.q21_bad = reinterpret_cast<const int*>(L.q21 + lut_q21_words(S));
+  if (getenv("VRGDG_NO_Q21")) { L.q21 = nullptr; L.q21_bad = nullptr; }
   for (int i = 0; i < 3; ++i) { L.dmin[i] = dmin[i]; L.dspan[i] = dspan[i]; }
   L.blend = blend; L.one_minus_blend = omb;
   L.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f) ? 1 : 0;
@@ -165,7 +172,7 @@ int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int64_t vrgdg_lut3d_packed_bytes(int lut_size) {
   if (lut_size < 2 || lut_size > 256) return 0;
-  return (int64_t)lut_size * lut_size * lut_size * LUT_CELL_FLOATS * (int64_t)sizeof(float);
+  return (int64_t)(lut_cells_floats(lut_size) + lut_q21_words(lut_size)) * 4 + 32;
 }
 
 int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream) {
@@ -176,7 +183,11 @@ int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream
   int rc = get_ctx(stream, ctx);
   if (rc) return rc;
   const int n = lut_size * lut_size * lut_size;
-  k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, lut_size);
+  uint32_t* q21 = reinterpret_cast<uint32_t*>(packed + lut_cells_floats(lut_size));
+  int* bad = reinterpret_cast<int*>(q21 + lut_q21_words(lut_size));
+  cudaError_t e0 = cudaMemsetAsync(bad, 0, 32, ctx.stream);
+  if (e0 != cudaSuccess) return fail_cuda(e0, "vrgdg_lut3d_pack");
+  k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, q21, bad, lut_size);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lut3d_pack");
@@ -342,7 +353,7 @@ int vrgdg_colormatch_apply(const void* in, void* out, int B, int H, int W, int d
   return VRGDG_OK;
 }
 
-static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, PointParams& P, int& mask, bool& exact, const void* ext_noise) {
+static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, PointParams& P, int& mask, bool& exact, const void* ext_noise, bool fast) {
   zero_point(P, B, H, W);
   mask = 0;
   if (d->grain_enabled) {
@@ -366,14 +377,14 @@ static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, Po
     fill_lut(P.lut, d->lut, d->lut_size, d->lut_dmin, d->lut_dspan, d->lut_blend, d->lut_one_minus_blend);
   }
   // exact arithmetic unless the chain draws its own noise (then only the noise-free stages stay exact in k_point<.., true>)
-  exact = !(d->grain_enabled && ext_noise == nullptr);
+  exact = !(d->grain_enabled && (ext_noise == nullptr || fast));
   return VRGDG_OK;
 }
 
 /* ext noise for the chain's first grain is passed through an environment-independent side door:
  * vrgdg_chain_apply_ext (test hook used by the parity tests, same kernels). */
 static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
-                            const void* ext_noise, void* stream) {
+                            const void* ext_noise, bool fast, void* stream) {
   if (!d) return fail(VRGDG_E_INVALID, "vrgdg_chain_apply: null descriptor");
   int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_apply");
   if (rc) return rc;
@@ -387,7 +398,7 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
   memset(&Q, 0, sizeof(Q));
   int mask = 0;
   bool exact = true;
-  if ((rc = chain_point_params(d, B, H, W, Q.P, mask, exact, ext_noise))) return rc;
+  if ((rc = chain_point_params(d, B, H, W, Q.P, mask, exact, ext_noise, fast))) return rc;
   const bool need_tile = d->stencil_op != VRGDG_STENCIL_NONE || d->post_grain_enabled;
   if (!need_tile) {
     if (mask == 0) {   // nothing enabled: copy
@@ -412,14 +423,14 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
 }
 
 int vrgdg_chain_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, void* stream) {
-  return chain_apply_impl(in, out, B, H, W, dtype, desc, nullptr, stream);
+  return chain_apply_impl(in, out, B, H, W, dtype, desc, nullptr, false, stream);
 }
 
 /* same as vrgdg_chain_apply with the first grain stage reading N(0,1) from ext_noise ([B,H,W,3], frame dtype);
  * exists so that the fused chain can be compared bit-for-bit in arithmetic with the reference composition. */
 int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
-                          const void* ext_noise, void* stream) {
-  return chain_apply_impl(in, out, B, H, W, dtype, desc, ext_noise, stream);
+                          const void* ext_noise, int flags, void* stream) {
+  return chain_apply_impl(in, out, B, H, W, dtype, desc, ext_noise, (flags & VRGDG_CHAIN_FAST_MATH) != 0, stream);
 }
 
 int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, double* sums,

@@ -53,7 +53,7 @@ struct PointParams {
 // One pixel through the enabled stages; (zr,zg,zb) = this pixel's N(0,1) triple (generator or external).
 template <int MASK, bool EXACT>
 __device__ __forceinline__ void process_pixel(const PointParams& P, const float* cmp, float zr, float zg, float zb,
-                                              float& r, float& g, float& b) {
+                                              float& r, float& g, float& b, bool use21 = false) {
   if (MASK & ST_GRAIN) {
     if (EXACT) grain_blend_exact(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
     else grain_blend_fast(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
@@ -63,13 +63,20 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const float*
   }
   if (MASK & ST_LUT) {
     float x0 = r, x1 = g, x2 = b;
-    lut3d_eval<EXACT>(P.lut, r, g, b);
+    if (!EXACT && use21) lut3d_eval21(P.lut, r, g, b);      // uniform branch: fast table, only when every value is in [0,1]
+    else lut3d_eval<EXACT>(P.lut, r, g, b);
     if (P.lut.blend < 1.0f) {
       r = lut_blend<EXACT>(x0, r, P.lut.blend, P.lut.one_minus_blend);
       g = lut_blend<EXACT>(x1, g, P.lut.blend, P.lut.one_minus_blend);
       b = lut_blend<EXACT>(x2, b, P.lut.blend, P.lut.one_minus_blend);
     }
   }
+}
+
+template <int MASK, bool EXACT>
+__device__ __forceinline__ bool lut_use21(const PointParams& P) {
+  if (EXACT || !(MASK & ST_LUT) || P.lut.q21 == nullptr) return false;
+  return __ldg(P.lut.q21_bad) == 0;
 }
 
 // =====================================================================================================
@@ -85,6 +92,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
   constexpr int NE = PX * 3;
   constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
   const bool has_ext = GRAIN && (P.ext_noise != nullptr);
+  const bool use21 = lut_use21<MASK, EXACT>(P);
   for (int64_t vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const int frame = (int)(vb / blocks_per_frame);
     const int bif = (int)(vb - (int64_t)frame * blocks_per_frame);
@@ -133,8 +141,8 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
             grain_pair_normals(grain_pair_bits(P.gkey, gf, (x >> 1) + (uint32_t)(j >> 1), y), z);
           }
         }
-        process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], v[3 * j], v[3 * j + 1], v[3 * j + 2]);
-        process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], v[3 * j + 3], v[3 * j + 4], v[3 * j + 5]);
+        process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], v[3 * j], v[3 * j + 1], v[3 * j + 2], use21);
+        process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], v[3 * j + 3], v[3 * j + 4], v[3 * j + 5], use21);
       }
       union { uint4 q[3]; T e[NE]; } u;
 #pragma unroll
@@ -147,7 +155,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         if (has_ext) { zr = nz[0]; zg = nz[1]; zb = nz[2]; }
         else grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
       }
-      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2]);
+      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2], use21);
 #pragma unroll
       for (int i = 0; i < NE; ++i) out[e0 + i] = Elem<T>::st(v[i]);
     }
@@ -549,6 +557,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
+      const bool use21 = lut_use21<MASK, EXACT>(P);
       const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
       for (int i = tid; i < ROWS * C::PAIRS; i += NT) {
         const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
@@ -574,9 +583,9 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
               grain_pair_normals(grain_pair_bits(P.gkey, gf, (uint32_t)pair, (uint32_t)y), z);
             }
           }
-          if (in_a) process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], e[0], e[1], e[2]);
+          if (in_a) process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], e[0], e[1], e[2], use21);
           else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
-          if (in_b) process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], e[3], e[4], e[5]);
+          if (in_b) process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], e[3], e[4], e[5], use21);
           else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
         if (WORK) {
@@ -686,7 +695,7 @@ static __global__ void k_moments_final(const double* __restrict__ partials, int 
   }
 }
 
-// params[b] = {mu_img[3], sd_img[3], mu_ref[3], sd_ref[3]};  sd = sqrt(unbiased var) + 1e-5  (nodes.py:99-100,109-110)
+// params[b] = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]};  sd = sqrt(unbiased var) + 1e-5  (nodes.py:99-100,109-110)
 static __global__ void k_colormatch_params(const double* __restrict__ fs, int B, const double* __restrict__ rs, int n_ref,
                                     float* __restrict__ params) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -698,26 +707,35 @@ static __global__ void k_colormatch_params(const double* __restrict__ fs, int B,
   for (int c = 0; c < 3; ++c) {
     double n = f[0], m = f[1 + c] / n;
     double var = (f[4 + c] - f[1 + c] * m) / (n - 1.0);
-    p[c] = (float)m;
-    p[3 + c] = __fadd_rn((float)sqrt(var > 0 ? var : 0.0), 1e-5f);
+    const float sd = __fadd_rn((float)sqrt(var > 0 ? var : 0.0), 1e-5f);        // fp32 std + 1e-5 as the reference forms it
     double nr = r[0], mr = r[1 + c] / nr;
     double varr = (r[4 + c] - r[1 + c] * mr) / (nr - 1.0);
+    const float sdr = __fadd_rn((float)sqrt(varr > 0 ? varr : 0.0), 1e-5f);
+    p[c] = (float)m;
+    p[3 + c] = (float)((double)sdr / (double)sd);
     p[6 + c] = (float)mr;
-    p[9 + c] = __fadd_rn((float)sqrt(varr > 0 ? varr : 0.0), 1e-5f);
+    p[9 + c] = sd;
   }
 }
 
-// reference-layout table [S][S][S][3] -> cell table (see vrgdg_math.cuh)
+// reference-layout table [S][S][S][3] -> fp32 cell table + unorm21 cell table + count of values outside [0,1]
 static __global__ void __launch_bounds__(256)
-k_lut_pack(const float* __restrict__ lut3, float* __restrict__ packed, int S) {
+k_lut_pack(const float* __restrict__ lut3, float* __restrict__ cells, uint32_t* __restrict__ q21, int* __restrict__ bad, int S) {
   const int n = S * S * S;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const int r = i % S, g = (i / S) % S, b = i / (S * S);
     float e[LUT_CELL_FLOATS];
     lut_pack_entry(lut3, S, b, g, r, e);
-    float4* d = reinterpret_cast<float4*>(packed + (size_t)i * LUT_CELL_FLOATS);
+    float4* d = reinterpret_cast<float4*>(cells + (size_t)i * LUT_CELL_FLOATS);
 #pragma unroll
     for (int k = 0; k < LUT_CELL_FLOATS / 4; ++k) d[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+    uint32_t w[16];
+    int isbad = 0;
+    lut_pack_entry21(e, w, isbad);
+    uint4* dq = reinterpret_cast<uint4*>(q21 + (size_t)i * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dq[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    if (isbad) atomicAdd(bad, 1);
   }
 }
 

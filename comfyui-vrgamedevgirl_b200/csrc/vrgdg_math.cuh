@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 #include <math.h>
 
 #if defined(__CUDACC__)
@@ -206,6 +207,8 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 // 32-byte r-pair table = 60-65 Gpx/s on grained frames, 3 lookups/px with this layout = 73-84 Gpx/s, 24 scalar = 34).
 struct LutParams {
   const float* lut;      // cell table, S*S*S*24 floats
+  const uint32_t* q21;   // unorm21 cell table, S*S*S*16 words (fast variant, see lut3d_eval21), or null
+  const int* q21_bad;    // number of table values outside [0,1] found while packing: q21 is usable iff *q21_bad == 0
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -288,6 +291,75 @@ VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   r = o[0]; g = o[1]; b = o[2];
 }
 
+// ---- unorm21 cell table: the fast variant for fused chains that are tolerance-checked (1e-5), never for the
+// bit-exact LUT node.  8 corners x (3 x 21-bit unorm in two words) = 64 bytes per cell = TWO 256-bit loads per pixel
+// (the gather is L1-tag bound: 2 lookups instead of 3 = +30% on grained frames, profiles/).  Quantisation error of a
+// table value <= 0.5/2097151 = 2.4e-7, below the fp32 rounding noise of the lerps; only valid when every table value
+// lies in [0,1] (true for colour-grading LUTs; otherwise the fp32 cell table is used).
+constexpr float LUT_Q21_SCALE = 2097151.0f;            // 2^21 - 1
+
+VRGDG_HD void lut_pack_entry21(const float* cell24, uint32_t* dst16, int& bad) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = cell24[3 * k + c];
+      if (!(v >= 0.0f && v <= 1.0f)) bad = 1;
+      q[c] = (uint32_t)(clamp01(v) * LUT_Q21_SCALE + 0.5f);
+    }
+    dst16[2 * k] = q[0] | (q[1] << 21);
+    dst16[2 * k + 1] = (q[1] >> 11) | (q[2] << 10);
+  }
+}
+
+VRGDG_HD void lut_dec21(uint32_t w0, uint32_t w1, float& r, float& g, float& b) {
+  const uint32_t M = 0x1FFFFFu;
+#if defined(__CUDA_ARCH__)
+  const uint32_t C = 0x4B000000u;                      // as_float(C | k) - 2^23 == float(k) for k < 2^23: no I2F on the quarter-rate pipe
+  r = __uint_as_float((w0 & M) | C) - 8388608.0f;
+  g = __uint_as_float((__funnelshift_r(w0, w1, 21) & M) | C) - 8388608.0f;
+  b = __uint_as_float(((w1 >> 10) & M) | C) - 8388608.0f;
+#else
+  r = (float)(w0 & M);
+  g = (float)(((w0 >> 21) | (w1 << 11)) & M);
+  b = (float)((w1 >> 10) & M);
+#endif
+}
+
+VRGDG_HD void lut3d_eval21(const LutParams& P, float& r, float& g, float& b) {
+  int r0, r1, g0, g1, b0, b1;
+  float fr, fg, fb;
+  lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
+  lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
+  lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
+  (void)r1; (void)g1; (void)b1;
+  const float* p = reinterpret_cast<const float*>(P.q21 + (size_t)((b0 * P.S + g0) * P.S + r0) * 16);
+  const F8 lo = lut_load8(p), hi = lut_load8(p + 8);
+  float v[8][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#if defined(__CUDA_ARCH__)
+    lut_dec21(__float_as_uint(lo.v[2 * k]), __float_as_uint(lo.v[2 * k + 1]), v[k][0], v[k][1], v[k][2]);
+    lut_dec21(__float_as_uint(hi.v[2 * k]), __float_as_uint(hi.v[2 * k + 1]), v[4 + k][0], v[4 + k][1], v[4 + k][2]);
+#else
+    uint32_t a0, a1, c0, c1;
+    memcpy(&a0, &lo.v[2 * k], 4); memcpy(&a1, &lo.v[2 * k + 1], 4); memcpy(&c0, &hi.v[2 * k], 4); memcpy(&c1, &hi.v[2 * k + 1], 4);
+    lut_dec21(a0, a1, v[k][0], v[k][1], v[k][2]);
+    lut_dec21(c0, c1, v[4 + k][0], v[4 + k][1], v[4 + k][2]);
+#endif
+  }
+  float o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {       // corner order c000 c100 c010 c110 | c001 c101 c011 c111
+    const float c00 = fmaf(fb, v[4][ch] - v[0][ch], v[0][ch]), c10 = fmaf(fb, v[5][ch] - v[1][ch], v[1][ch]);
+    const float c01 = fmaf(fb, v[6][ch] - v[2][ch], v[2][ch]), c11 = fmaf(fb, v[7][ch] - v[3][ch], v[3][ch]);
+    const float c0 = fmaf(fg, c01 - c00, c00), c1 = fmaf(fg, c11 - c10, c10);
+    o[ch] = clamp01(fmaf(fr, c1 - c0, c0) * (1.0f / LUT_Q21_SCALE));
+  }
+  r = o[0]; g = o[1]; b = o[2];
+}
+
 // strength blend of apply_lut (:355-359) on already-rounded LUT output `y` and input `x`
 template <bool EXACT>
 VRGDG_HD float lut_blend(float x, float y, float blend, float omb) {
@@ -345,61 +417,60 @@ VRGDG_HD float pow_inv2p4(float x) {
   return (y2 * y2) * y;
 }
 
+// Divisions by constants are multiplications by the rounded reciprocal (<= 1 ulp from the divided value); the colour-match
+// path is tolerance-based (1e-5 on RGB), not bit-pinned (kornia itself is unpinned), measured error vs the oracle ~7e-7.
 VRGDG_HD float srgb_to_linear(float c) {
   // where(c > 0.04045, ((c + 0.055) / 1.055) ** 2.4, c / 12.92)
-  return (c > 0.04045f) ? pow_2p4(divx(addx(c, 0.055f), 1.055f)) : divx(c, 12.92f);
+  return (c > 0.04045f) ? pow_2p4((c + 0.055f) * (float)(1.0 / 1.055)) : c * (float)(1.0 / 12.92);
 }
 VRGDG_HD float linear_to_srgb(float l) {
   // where(l > 0.0031308, 1.055 * clamp(l, min=thr) ** (1/2.4) - 0.055, 12.92 * l)
-  return (l > 0.0031308f) ? subx(mulx(1.055f, pow_inv2p4(fmaxf(l, 0.0031308f))), 0.055f)
-                          : mulx(12.92f, l);
+  return (l > 0.0031308f) ? fmaf(1.055f, pow_inv2p4(fmaxf(l, 0.0031308f)), -0.055f) : 12.92f * l;
 }
 VRGDG_HD float lab_f(float t) {
   // where(t > 0.008856, clamp(t, min=0.008856) ** (1/3), 7.787 t + 4/29)
-  return (t > 0.008856f) ? cbrt_pos(fmaxf(t, 0.008856f))
-                         : addx(mulx(7.787f, t), (float)(4.0 / 29.0));
+  return (t > 0.008856f) ? cbrt_pos(fmaxf(t, 0.008856f)) : fmaf(7.787f, t, (float)(4.0 / 29.0));
 }
 VRGDG_HD void rgb_to_lab(float r, float g, float b, float& L, float& A, float& Bv) {
   float lr = srgb_to_linear(r), lg = srgb_to_linear(g), lb = srgb_to_linear(b);
-  float x = addx(addx(mulx(0.412453f, lr), mulx(0.357580f, lg)), mulx(0.180423f, lb));
-  float y = addx(addx(mulx(0.212671f, lr), mulx(0.715160f, lg)), mulx(0.072169f, lb));
-  float z = addx(addx(mulx(0.019334f, lr), mulx(0.119193f, lg)), mulx(0.950227f, lb));
-  float fx = lab_f(divx(x, 0.95047f));
+  float x = fmaf(0.180423f, lb, fmaf(0.357580f, lg, 0.412453f * lr));
+  float y = fmaf(0.072169f, lb, fmaf(0.715160f, lg, 0.212671f * lr));
+  float z = fmaf(0.950227f, lb, fmaf(0.119193f, lg, 0.019334f * lr));
+  float fx = lab_f(x * (float)(1.0 / 0.95047));
   float fy = lab_f(y);                                 // y / 1.0
-  float fz = lab_f(divx(z, 1.08883f));
-  L = subx(mulx(116.0f, fy), 16.0f);
-  A = mulx(500.0f, subx(fx, fy));
-  Bv = mulx(200.0f, subx(fy, fz));
+  float fz = lab_f(z * (float)(1.0 / 1.08883));
+  L = fmaf(116.0f, fy, -16.0f);
+  A = 500.0f * (fx - fy);
+  Bv = 200.0f * (fy - fz);
 }
 VRGDG_HD float lab_finv(float f) {
   // where(f > 0.2068966, f ** 3, (f - 4/29) / 7.787)
-  // torch.pow(x, 3.0) evaluates x*x*x
-  return (f > 0.2068966f) ? mulx(mulx(f, f), f) : divx(subx(f, (float)(4.0 / 29.0)), 7.787f);
+  return (f > 0.2068966f) ? (f * f) * f : (f - (float)(4.0 / 29.0)) * (float)(1.0 / 7.787);
 }
 VRGDG_HD void lab_to_rgb(float L, float A, float Bv, float& r, float& g, float& b) {
-  float fy = divx(addx(L, 16.0f), 116.0f);
-  float fx = addx(divx(A, 500.0f), fy);
-  float fz = fmaxf(subx(fy, divx(Bv, 200.0f)), 0.0f);
-  float x = mulx(lab_finv(fx), 0.95047f);
+  float fy = (L + 16.0f) * (float)(1.0 / 116.0);
+  float fx = fmaf(A, (float)(1.0 / 500.0), fy);
+  float fz = fmaxf(fmaf(Bv, (float)(-1.0 / 200.0), fy), 0.0f);
+  float x = lab_finv(fx) * 0.95047f;
   float y = lab_finv(fy);                              // * 1.0
-  float z = mulx(lab_finv(fz), 1.08883f);
-  float lr = addx(addx(mulx(3.2404813432005266f, x), mulx(-1.5371515162713185f, y)), mulx(-0.4985363261688878f, z));
-  float lg = addx(addx(mulx(-0.9692549499965682f, x), mulx(1.8759900014898907f, y)), mulx(0.0415559265582928f, z));
-  float lb = addx(addx(mulx(0.0556466391351772f, x), mulx(-0.2040413383665112f, y)), mulx(1.0573110696453443f, z));
+  float z = lab_finv(fz) * 1.08883f;
+  float lr = fmaf(-0.4985363261688878f, z, fmaf(-1.5371515162713185f, y, 3.2404813432005266f * x));
+  float lg = fmaf(0.0415559265582928f, z, fmaf(1.8759900014898907f, y, -0.9692549499965682f * x));
+  float lb = fmaf(1.0573110696453443f, z, fmaf(-0.2040413383665112f, y, 0.0556466391351772f * x));
   r = clamp01(linear_to_srgb(lr));
   g = clamp01(linear_to_srgb(lg));
   b = clamp01(linear_to_srgb(lb));
 }
 
 // nodes.py:112-115: matched = (lab - mu)/sd * sd_ref + mu_ref ; blended = t*matched + (1-t)*lab
-// p = {mu_img[3], sd_img[3], mu_ref[3], sd_ref[3]}
+// p = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]}  (the ratio is formed once per frame in fp64)
 VRGDG_HD void colormatch_pixel(float& r, float& g, float& b, const float* p, float t, float omt) {
   float lab[3];
   rgb_to_lab(r, g, b, lab[0], lab[1], lab[2]);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float m = addx(mulx(divx(subx(lab[c], p[c]), p[3 + c]), p[9 + c]), p[6 + c]);
-    lab[c] = addx(mulx(t, m), mulx(omt, lab[c]));
+    float m = fmaf(lab[c] - p[c], p[3 + c], p[6 + c]);
+    lab[c] = fmaf(t, m, omt * lab[c]);
   }
   lab_to_rgb(lab[0], lab[1], lab[2], r, g, b);
 }

@@ -119,7 +119,7 @@ def lab_moments(images, row0=0, rows=None):
 
 
 def colormatch_params(frame_sums, ref_sums):
-    """[B,7] + [1|B,7] float64 CUDA -> [B,12] float32 {mu_img, sd_img, mu_ref, sd_ref}."""
+    """[B,7] + [1|B,7] float64 CUDA -> [B,12] float32 {mu_img, sd_ref/sd_img, mu_ref, sd_img}."""
     fs = frame_sums.contiguous()
     rs = ref_sums.to(fs.device).contiguous()
     if fs.dtype != torch.float64 or rs.dtype != torch.float64 or fs.ndim != 2 or fs.shape[1] != 7 or rs.ndim != 2 or rs.shape[1] != 7:
@@ -148,7 +148,7 @@ def colormatch_apply(images, params, t_strength, one_minus_t):
     return out
 
 
-def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None):
+def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=False):
     """Run the fused chain described by a ChainDesc.  `keepalive` holds tensors the descriptor points to."""
     t = _frames(images)
     B, H, W, _ = t.shape
@@ -161,7 +161,7 @@ def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None):
             if n.shape != t.shape or n.dtype != t.dtype or n.device != t.device:
                 raise ValueError("vrgdg_b200: ext_noise must match images in shape, dtype and device")
             nv.check(lib.vrgdg_chain_apply_ext(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(n),
-                                               nv.stream_ptr(t.device)))
+                                               nv.CHAIN_FAST_MATH if fast_math else 0, nv.stream_ptr(t.device)))
         else:
             nv.check(lib.vrgdg_chain_apply(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.stream_ptr(t.device)))
     del keepalive

@@ -88,7 +88,9 @@ VRGDG_API const char* vrgdg_last_tile_path(void);
 VRGDG_API int64_t vrgdg_lut3d_packed_bytes(int lut_size);
 /* lut: device [S,S,S,3] fp32 (reference layout); packed: device buffer of vrgdg_lut3d_packed_bytes(S), 32-byte aligned.
  * Entry (b,g,r) of the packed table = the 8 corners of the cell whose origin is (b,g,r) (neighbours clamped to S-1), 24 floats
- * = 96 bytes: a pixel's whole trilinear stencil arrives with three consecutive 256-bit loads. */
+ * = 96 bytes: a pixel's whole trilinear stencil arrives with three consecutive 256-bit loads.  The buffer also holds a
+ * 64-byte-per-cell unorm21 copy (two loads per pixel, |error| <= 2.4e-7) that only the tolerance-checked fused chains with
+ * in-kernel noise use, and only when every table value lies in [0,1]; the LUT entry point always reads the fp32 cells. */
 VRGDG_API int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream);
 VRGDG_API int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype,
                       const float* lut_packed, int lut_size,
@@ -119,7 +121,8 @@ VRGDG_API int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, i
  * Step 1: per-frame raw LAB sums over image rows [row0,row0+rows): sums[b] = {n, S_L, S_a, S_b, S_LL, S_aa, S_bb}
  *         (7 doubles per frame; fixed-order two-level reduction, deterministic).  Row ranges exist so the
  *         reference image can be sharded by rows across ranks and merged by addition.
- * Step 2: params[b] = {mu_img[3], sd_img[3], mu_ref[3], sd_ref[3]} fp32, sd = unbiased std + 1e-5 (:99-100,:109-110).
+ * Step 2: params[b] = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]} fp32, sd = unbiased std + 1e-5 (:99-100,:109-110);
+ *         opaque to the caller, consumed by vrgdg_colormatch_apply / the chain.
  *         n_ref is 1 (broadcast) or B.
  * Step 3: out = clamp(lab_to_rgb(t*((lab-mu)/sd*sd_ref+mu_ref) + (1-t)*lab)). */
 VRGDG_API int64_t vrgdg_lab_moments_scratch_bytes(int B);
@@ -170,8 +173,12 @@ VRGDG_API int vrgdg_chain_apply(const void* in, void* out, int B, int H, int W, 
 /* vrgdg_chain_apply with the first grain stage reading N(0,1) from ext_noise ([B,H,W,3], frame dtype) instead
  * of the in-kernel generator: lets the fused chain be compared with the reference composition on the same
  * noise tensor (nodes.py:51 draws it from torch's generator, which no CUDA kernel can reproduce). */
+/* flags: VRGDG_CHAIN_FAST_MATH = run the arithmetic variant vrgdg_chain_apply uses when it draws its own noise (FMA-contracted
+ * grain blend and LUT lerps) on the external noise, so that exactly the benchmarked code path can be compared with the
+ * reference composition (<= 1e-5); 0 = one rounding per reference op (bit-exact stages). */
+#define VRGDG_CHAIN_FAST_MATH 1
 VRGDG_API int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int W, int dtype,
-                          const vrgdg_chain_desc* desc, const void* ext_noise, void* stream);
+                          const vrgdg_chain_desc* desc, const void* ext_noise, int flags, void* stream);
 
 /* LAB sums of grain(x) (stage 1 of desc only) so that colour match can follow grain inside the chain
  * without materialising the grained frames. */

@@ -53,15 +53,20 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
   float* packed = new float[(size_t)S * S * S * LUT_CELL_FLOATS];
   for (int bb = 0; bb < S; ++bb) for (int gg = 0; gg < S; ++gg) for (int rr = 0; rr < S; ++rr)
     lut_pack_entry(lut, S, bb, gg, rr, packed + ((size_t)(bb * S + gg) * S + rr) * LUT_CELL_FLOATS);
+  uint32_t* q21 = new uint32_t[(size_t)S * S * S * 16];
+  int bad = 0;
+  for (size_t c = 0; c < (size_t)S * S * S; ++c) lut_pack_entry21(packed + c * LUT_CELL_FLOATS, q21 + c * 16, bad);
   LutParams P;
-  P.lut = packed; P.S = S; P.smax = (float)(S - 1);
+  P.lut = packed; P.q21 = q21; P.q21_bad = &bad; P.S = S; P.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
   P.blend = blend; P.one_minus_blend = omb;
   P.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f);
   for (int64_t i = 0; i < n; ++i) {
     float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
     float x0 = r, x1 = g, x2 = b;
-    if (exact) lut3d_eval<true>(P, r, g, b); else lut3d_eval<false>(P, r, g, b);
+    if (exact == 1) lut3d_eval<true>(P, r, g, b);
+    else if (exact == 2 && bad == 0) lut3d_eval21(P, r, g, b);       // unorm21 fast table
+    else lut3d_eval<false>(P, r, g, b);
     if (blend < 1.0f) {
       if (exact) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }
       else { r = lut_blend<false>(x0, r, blend, omb); g = lut_blend<false>(x1, g, blend, omb); b = lut_blend<false>(x2, b, blend, omb); }
@@ -69,6 +74,7 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
     out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
   }
   delete[] packed;
+  delete[] q21;
 }
 
 void hc_rgb_to_lab(const float* in, float* out, int64_t n) {

@@ -99,6 +99,8 @@ def test_lut_eval_exact_is_bit_identical(hostcheck, oracle):
         assert np.array_equal(o, flat(g[f"{key}__s3p5"])), fname
         hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 0)      # contracted variant
         assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 2)      # unorm21 fast table
+        assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
 
 
 def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
@@ -119,7 +121,8 @@ def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
             n, m = s[0], s[1:4] / s[0]
             var = (s[4:7] - s[1:4] * m) / (n - 1)
             return m.astype(np.float32), np.sqrt(var).astype(np.float32) + np.float32(1e-5)
-        params = np.concatenate(stats(fs) + stats(ref_s)).astype(np.float32)
+        (mi, si), (mr, sr) = stats(fs), stats(ref_s)
+        params = np.concatenate([mi, (sr.astype(np.float64) / si.astype(np.float64)).astype(np.float32), mr, si]).astype(np.float32)
         xin = flat(c["x"][b])
         out = np.zeros_like(xin)
         hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 1.0, 0.0)
