@@ -130,6 +130,7 @@ int run_tile(const void* in, void* out, int B, int H, int W, int dtype, TilePara
   (void)DISPATCH_DTYPE(dtype, GEO);
 #undef GEO
   Q.total_tiles = (int64_t)B * Q.tiles_x * Q.tiles_y;
+  if (Q.total_tiles >= ((int64_t)1 << 31)) return fail(VRGDG_E_UNSUPPORTED, "batch of %d frames has too many tiles for one launch; split it", B);
   CUtensorMap map;
   bool tma = build_tmap(&map, in, B, H, Q.RW, dtype, bx, by);
   Q.use_tma = tma ? 1 : 0;

@@ -73,6 +73,19 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const float*
   }
 }
 
+// two pixels at once: all per-pixel stages up to the LUT, then BOTH gathers issued before either is consumed
+template <int MASK, bool EXACT>
+__device__ __forceinline__ void process_pair(const PointParams& P, const float* cmp, const float* z, float* p, bool use21) {
+  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[0], z[1], z[2], p[0], p[1], p[2]);
+  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[3], z[4], z[5], p[3], p[4], p[5]);
+  if (MASK & ST_LUT) {
+    float a0 = p[0], a1 = p[1], a2 = p[2], b0 = p[3], b1 = p[4], b2 = p[5];
+    process_pixel<ST_LUT, EXACT>(P, cmp, 0.f, 0.f, 0.f, a0, a1, a2, use21);
+    process_pixel<ST_LUT, EXACT>(P, cmp, 0.f, 0.f, 0.f, b0, b1, b2, use21);
+    p[0] = a0; p[1] = a1; p[2] = a2; p[3] = b0; p[4] = b1; p[5] = b2;
+  }
+}
+
 template <int MASK, bool EXACT>
 __device__ __forceinline__ bool lut_use21(const PointParams& P) {
   if (EXACT || !(MASK & ST_LUT) || P.lut.q21 == nullptr) return false;
@@ -485,15 +498,18 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
   constexpr bool WORK = C::WORK;                           // separate fp32 tile for the pre-stage results
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // 128-byte alignment by offset (keeps the pointer in the shared address space -> LDS/STS, not generic LD/ST)
+  const uint32_t smem_a = smem_u32(smem_raw);
+  uint8_t* base = smem_raw + (((smem_a + 127u) & ~127u) - smem_a);
   T* stage0 = reinterpret_cast<T*>(base);
   float* work = reinterpret_cast<float*>(base + (size_t)NS * C::STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NS * C::STAGE_BYTES + (WORK ? ROWS * BX * 4 : 0));
 
   const int tid = threadIdx.x;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
-  const int64_t n_my = (Q.total_tiles > first) ? (Q.total_tiles - first + stride - 1) / stride : 0;
-  const int tiles_per_frame = Q.tiles_x * Q.tiles_y;
+  // total_tiles < 2^31 (checked on the host): 32-bit tile arithmetic, no 64-bit divisions per tile
+  const uint32_t first = blockIdx.x, stride = gridDim.x, total = (uint32_t)Q.total_tiles;
+  const uint32_t n_my = (total > first) ? (total - first + stride - 1) / stride : 0;
+  const uint32_t tiles_per_frame = (uint32_t)(Q.tiles_x * Q.tiles_y);
   const bool tma = Q.use_tma != 0;
 
   if (tma && tid == 0) {
@@ -504,15 +520,16 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
   }
   __syncthreads();
 
-  auto tile_coords = [&](int64_t k, int& frame, int& y0, int& x0e) {
-    int64_t t = first + k * stride;
-    frame = (int)(t / tiles_per_frame);
-    int rem = (int)(t - (int64_t)frame * tiles_per_frame);
-    int ty = rem / Q.tiles_x;
-    y0 = ty * TY;
-    x0e = (rem - ty * Q.tiles_x) * TXE;
+  auto tile_coords = [&](uint32_t k, int& frame, int& y0, int& x0e) {
+    const uint32_t t = first + k * stride;
+    const uint32_t f = t / tiles_per_frame;
+    const uint32_t rem = t - f * tiles_per_frame;
+    const uint32_t ty = rem / (uint32_t)Q.tiles_x;
+    frame = (int)f;
+    y0 = (int)ty * TY;
+    x0e = (int)(rem - ty * (uint32_t)Q.tiles_x) * TXE;
   };
-  auto issue = [&](int64_t k) {
+  auto issue = [&](uint32_t k) {
     int frame, y0, x0e;
     tile_coords(k, frame, y0, x0e);
     int s = (int)(k % NS);
@@ -521,10 +538,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
   };
 
   if (tma && tid == 0) {
-    for (int64_t k = 0; k < NS - 1 && k < n_my; ++k) issue(k);
+    for (uint32_t k = 0; k < NS - 1 && k < n_my; ++k) issue(k);
   }
 
-  for (int64_t k = 0; k < n_my; ++k) {
+  for (uint32_t k = 0; k < n_my; ++k) {
     int frame, y0, x0e;
     tile_coords(k, frame, y0, x0e);
     const int s = tma ? (int)(k % NS) : 0;
@@ -583,10 +600,12 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
               grain_pair_normals(grain_pair_bits(P.gkey, gf, (uint32_t)pair, (uint32_t)y), z);
             }
           }
-          if (in_a) process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], e[0], e[1], e[2], use21);
-          else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
-          if (in_b) process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], e[3], e[4], e[5], use21);
-          else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
+          // both pixels go through the stages unconditionally (their 2 x 3 LUT loads are then in flight together; a pixel
+          // outside the image computes on staged zeros and is discarded) - the branchy form serialised the two gathers
+          float p[6] = {e[0], e[1], e[2], e[3], e[4], e[5]};
+          process_pair<MASK, EXACT>(P, cmp, z, p, use21);
+          if (in_a) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; } else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
+          if (in_b) { e[3] = p[3]; e[4] = p[4]; e[5] = p[5]; } else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
         if (WORK) {
           pair_store6(work + so, kx > 0, e);                       // zeros for pixels outside the image
