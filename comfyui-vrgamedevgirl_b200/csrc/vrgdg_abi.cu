@@ -103,15 +103,10 @@ bool build_tmap(CUtensorMap* map, const void* in, int B, int H, int RW, int dtyp
   return r == CUDA_SUCCESS;
 }
 
-// packed LUT buffer = [fp32 cells: S^3*24 floats][unorm21 cells: S^3*16 words][bad-value count: 1 int, padded to 32 bytes]
 size_t lut_cells_floats(int S) { return (size_t)S * S * S * LUT_CELL_FLOATS; }
-size_t lut_q21_words(int S) { return (size_t)S * S * S * 16; }
 
 void fill_lut(LutParams& L, const float* lut, int S, const float* dmin, const float* dspan, float blend, float omb) {
   L.lut = lut; L.S = S; L.smax = (float)(S - 1);
-  L.q21 = reinterpret_cast<const uint32_t*>(lut + lut_cells_floats(S));
-  L.q21_bad = reinterpret_cast<const int*>(L.q21 + lut_q21_words(S));
-  if (getenv("VRGDG_NO_Q21")) { L.q21 = nullptr; L.q21_bad = nullptr; }
   for (int i = 0; i < 3; ++i) { L.dmin[i] = dmin[i]; L.dspan[i] = dspan[i]; }
   L.blend = blend; L.one_minus_blend = omb;
   L.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f) ? 1 : 0;
@@ -173,7 +168,7 @@ int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int64_t vrgdg_lut3d_packed_bytes(int lut_size) {
   if (lut_size < 2 || lut_size > 256) return 0;
-  return (int64_t)(lut_cells_floats(lut_size) + lut_q21_words(lut_size)) * 4 + 32;
+  return (int64_t)lut_cells_floats(lut_size) * 4;
 }
 
 int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream) {
@@ -184,11 +179,7 @@ int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream
   int rc = get_ctx(stream, ctx);
   if (rc) return rc;
   const int n = lut_size * lut_size * lut_size;
-  uint32_t* q21 = reinterpret_cast<uint32_t*>(packed + lut_cells_floats(lut_size));
-  int* bad = reinterpret_cast<int*>(q21 + lut_q21_words(lut_size));
-  cudaError_t e0 = cudaMemsetAsync(bad, 0, 32, ctx.stream);
-  if (e0 != cudaSuccess) return fail_cuda(e0, "vrgdg_lut3d_pack");
-  k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, q21, bad, lut_size);
+  k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, lut_size);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lut3d_pack");
@@ -287,6 +278,7 @@ int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, int dtype, 
   memset(&Q, 0, sizeof(Q));
   zero_point(Q.P, B, H, W);
   Q.op = op; Q.strength = strength; Q.border = border;
+  Q.exact_stencil = (dtype == VRGDG_F32) ? 1 : 0;     // fp32 frames: bit-identical to the NumPy nodes; 16-bit frames round once anyway
   return run_tile(in, out, B, H, W, dtype, Q, 0, true, ctx);
 }
 
@@ -416,6 +408,7 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
     return VRGDG_OK;
   }
   Q.op = d->stencil_op; Q.strength = d->stencil_strength; Q.border = d->stencil_border;
+  Q.exact_stencil = (exact && dtype == VRGDG_F32) ? 1 : 0;
   Q.post_enabled = d->post_grain_enabled ? 1 : 0;
   Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
   Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;

@@ -53,7 +53,7 @@ struct PointParams {
 // One pixel through the enabled stages; (zr,zg,zb) = this pixel's N(0,1) triple (generator or external).
 template <int MASK, bool EXACT>
 __device__ __forceinline__ void process_pixel(const PointParams& P, const float* cmp, float zr, float zg, float zb,
-                                              float& r, float& g, float& b, bool use21 = false) {
+                                              float& r, float& g, float& b) {
   if (MASK & ST_GRAIN) {
     if (EXACT) grain_blend_exact(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
     else grain_blend_fast(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
@@ -63,8 +63,7 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const float*
   }
   if (MASK & ST_LUT) {
     float x0 = r, x1 = g, x2 = b;
-    if (!EXACT && use21) lut3d_eval21(P.lut, r, g, b);      // uniform branch: fast table, only when every value is in [0,1]
-    else lut3d_eval<EXACT>(P.lut, r, g, b);
+    lut3d_eval<EXACT>(P.lut, r, g, b);
     if (P.lut.blend < 1.0f) {
       r = lut_blend<EXACT>(x0, r, P.lut.blend, P.lut.one_minus_blend);
       g = lut_blend<EXACT>(x1, g, P.lut.blend, P.lut.one_minus_blend);
@@ -75,21 +74,17 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const float*
 
 // two pixels at once: all per-pixel stages up to the LUT, then BOTH gathers issued before either is consumed
 template <int MASK, bool EXACT>
-__device__ __forceinline__ void process_pair(const PointParams& P, const float* cmp, const float* z, float* p, bool use21) {
+__device__ __forceinline__ void process_pair(const PointParams& P, const float* cmp, const float* z, float* p) {
   process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[0], z[1], z[2], p[0], p[1], p[2]);
   process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[3], z[4], z[5], p[3], p[4], p[5]);
   if (MASK & ST_LUT) {
-    float a0 = p[0], a1 = p[1], a2 = p[2], b0 = p[3], b1 = p[4], b2 = p[5];
-    process_pixel<ST_LUT, EXACT>(P, cmp, 0.f, 0.f, 0.f, a0, a1, a2, use21);
-    process_pixel<ST_LUT, EXACT>(P, cmp, 0.f, 0.f, 0.f, b0, b1, b2, use21);
-    p[0] = a0; p[1] = a1; p[2] = a2; p[3] = b0; p[4] = b1; p[5] = b2;
+    float x[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
+    lut3d_eval2<EXACT>(P.lut, p, p + 3);
+    if (P.lut.blend < 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) p[i] = lut_blend<EXACT>(x[i], p[i], P.lut.blend, P.lut.one_minus_blend);
+    }
   }
-}
-
-template <int MASK, bool EXACT>
-__device__ __forceinline__ bool lut_use21(const PointParams& P) {
-  if (EXACT || !(MASK & ST_LUT) || P.lut.q21 == nullptr) return false;
-  return __ldg(P.lut.q21_bad) == 0;
 }
 
 // =====================================================================================================
@@ -105,7 +100,6 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
   constexpr int NE = PX * 3;
   constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
   const bool has_ext = GRAIN && (P.ext_noise != nullptr);
-  const bool use21 = lut_use21<MASK, EXACT>(P);
   for (int64_t vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
     const int frame = (int)(vb / blocks_per_frame);
     const int bif = (int)(vb - (int64_t)frame * blocks_per_frame);
@@ -154,8 +148,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
             grain_pair_normals(grain_pair_bits(P.gkey, gf, (x >> 1) + (uint32_t)(j >> 1), y), z);
           }
         }
-        process_pixel<MASK, EXACT>(P, cmp, z[0], z[1], z[2], v[3 * j], v[3 * j + 1], v[3 * j + 2], use21);
-        process_pixel<MASK, EXACT>(P, cmp, z[3], z[4], z[5], v[3 * j + 3], v[3 * j + 4], v[3 * j + 5], use21);
+        process_pair<MASK, EXACT>(P, cmp, z, &v[3 * j]);
       }
       union { uint4 q[3]; T e[NE]; } u;
 #pragma unroll
@@ -168,7 +161,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         if (has_ext) { zr = nz[0]; zg = nz[1]; zb = nz[2]; }
         else grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
       }
-      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2], use21);
+      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2]);
 #pragma unroll
       for (int i = 0; i < NE; ++i) out[e0 + i] = Elem<T>::st(v[i]);
     }
@@ -264,6 +257,7 @@ struct TileParams {
   int64_t pframe0;
   int pseed_mode;
   GrainKey pkey;                // round keys of the post-grain generator
+  int exact_stencil;            // 1: reference evaluation order, one rounding per op (bit-exact NumPy-path results for fp32)
   int use_tma;                  // 0: cooperative bounds-checked loads (any alignment)
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
 };
@@ -281,7 +275,7 @@ template <typename T, int MASK> struct TileCfg {
   static constexpr int TXE = 240;                     // output elements per tile row (multiple of 6 and of VEC)
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
-  static constexpr int THREADS = HEAVY ? 512 : 256;
+  static constexpr int THREADS = HEAVY ? 480 : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
   static constexpr int MINB = HEAVY ? 1 : 2;
   static constexpr int COLS = TXE / VEC;              // threads across
   static constexpr int RG = (HEAVY ? 480 : 240) / COLS;   // row groups (active threads / COLS)
@@ -401,7 +395,7 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
   }
 }
 
-template <typename T, int OP, int MASK>
+template <typename T, int OP, int MASK, bool XS>
 __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
                                              int frame, int y0, int x0e) {
   using C = TileCfg<T, MASK>;
@@ -418,7 +412,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
     else load_window<T, VEC>(raw + srow * BX + PADL + f0, dst);
   };
   const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
-  if (OP == 1) {
+  if (OP == 1 && !XS) {
     // 3x3 box is separable: keep the horizontal 3-sums of the two previous rows (nodes.py:194-206)
     float h0[VEC], h1[VEC], c1[VEC], wr[WN];
     load_row(rbase, wr);
@@ -455,7 +449,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
       for (int e = 0; e < VEC; ++e) {
         float n[9] = {w[0][e], w[0][e + 3], w[0][e + 6], w[1][e], w[1][e + 3], w[1][e + 6],
                       w[2][e], w[2][e + 3], w[2][e + 6]};
-        o[e] = stencil_epilogue(OP, n, Q.strength);
+        o[e] = XS ? stencil_epilogue_exact(OP, n, Q.strength) : stencil_epilogue(OP, n, Q.strength);
       }
       if (Q.post_enabled) post_grain_elems<VEC>(Q, pgf, ge0, y, o);
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
@@ -574,8 +568,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
-      const bool use21 = lut_use21<MASK, EXACT>(P);
-      const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
+          const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
       for (int i = tid; i < ROWS * C::PAIRS; i += NT) {
         const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
         const int y = y0 - 1 + r, pair = pair0 + kx;
@@ -603,7 +596,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
           // both pixels go through the stages unconditionally (their 2 x 3 LUT loads are then in flight together; a pixel
           // outside the image computes on staged zeros and is discarded) - the branchy form serialised the two gathers
           float p[6] = {e[0], e[1], e[2], e[3], e[4], e[5]};
-          process_pair<MASK, EXACT>(P, cmp, z, p, use21);
+          process_pair<MASK, EXACT>(P, cmp, z, p);
           if (in_a) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; } else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
           if (in_b) { e[3] = p[3]; e[4] = p[4]; e[5] = p[5]; } else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
@@ -624,13 +617,24 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     // ---- 3x3 stencil, sliding 3-row register window, VEC outputs per thread per row ----
     {
       const float* wt = WORK ? work : nullptr;
-      switch (Q.op) {   // uniform; one specialised row loop per epilogue
-        case 1: stencil_rows<T, 1, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 2: stencil_rows<T, 2, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 3: stencil_rows<T, 3, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 4: stencil_rows<T, 4, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
-        case 5: stencil_rows<T, 5, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
-        default: stencil_rows<T, 0, MASK>(raw, wt, out, Q, frame, y0, x0e); break;
+      if (Q.exact_stencil) {   // uniform; one specialised row loop per epilogue and arithmetic variant
+        switch (Q.op) {
+          case 1: stencil_rows<T, 1, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 2: stencil_rows<T, 2, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 4: stencil_rows<T, 4, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          default: stencil_rows<T, 0, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+        }
+      } else {
+        switch (Q.op) {
+          case 1: stencil_rows<T, 1, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 2: stencil_rows<T, 2, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 4: stencil_rows<T, 4, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          default: stencil_rows<T, 0, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+        }
       }
     }
     if (tma) fence_proxy_async();   // generic-proxy writes to this stage happen-before its next async refill
@@ -737,9 +741,9 @@ static __global__ void k_colormatch_params(const double* __restrict__ fs, int B,
   }
 }
 
-// reference-layout table [S][S][S][3] -> fp32 cell table + unorm21 cell table + count of values outside [0,1]
+// reference-layout table [S][S][S][3] -> cell table (see vrgdg_math.cuh)
 static __global__ void __launch_bounds__(256)
-k_lut_pack(const float* __restrict__ lut3, float* __restrict__ cells, uint32_t* __restrict__ q21, int* __restrict__ bad, int S) {
+k_lut_pack(const float* __restrict__ lut3, float* __restrict__ cells, int S) {
   const int n = S * S * S;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
     const int r = i % S, g = (i / S) % S, b = i / (S * S);
@@ -748,13 +752,6 @@ k_lut_pack(const float* __restrict__ lut3, float* __restrict__ cells, uint32_t* 
     float4* d = reinterpret_cast<float4*>(cells + (size_t)i * LUT_CELL_FLOATS);
 #pragma unroll
     for (int k = 0; k < LUT_CELL_FLOATS / 4; ++k) d[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
-    uint32_t w[16];
-    int isbad = 0;
-    lut_pack_entry21(e, w, isbad);
-    uint4* dq = reinterpret_cast<uint4*>(q21 + (size_t)i * 16);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dq[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-    if (isbad) atomicAdd(bad, 1);
   }
 }
 

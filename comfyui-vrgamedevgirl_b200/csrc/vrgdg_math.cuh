@@ -207,8 +207,6 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 // 32-byte r-pair table = 60-65 Gpx/s on grained frames, 3 lookups/px with this layout = 73-84 Gpx/s, 24 scalar = 34).
 struct LutParams {
   const float* lut;      // cell table, S*S*S*24 floats
-  const uint32_t* q21;   // unorm21 cell table, S*S*S*16 words (fast variant, see lut3d_eval21), or null
-  const int* q21_bad;    // number of table values outside [0,1] found while packing: q21 is usable iff *q21_bad == 0
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -291,73 +289,48 @@ VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   r = o[0]; g = o[1]; b = o[2];
 }
 
-// ---- unorm21 cell table: the fast variant for fused chains that are tolerance-checked (1e-5), never for the
-// bit-exact LUT node.  8 corners x (3 x 21-bit unorm in two words) = 64 bytes per cell = TWO 256-bit loads per pixel
-// (the gather is L1-tag bound: 2 lookups instead of 3 = +30% on grained frames, profiles/).  Quantisation error of a
-// table value <= 0.5/2097151 = 2.4e-7, below the fp32 rounding noise of the lerps; only valid when every table value
-// lies in [0,1] (true for colour-grading LUTs; otherwise the fp32 cell table is used).
-constexpr float LUT_Q21_SCALE = 2097151.0f;            // 2^21 - 1
+// Two pixels at once: both address computations first, then all six 256-bit loads, then the lerps, so that the two
+// gathers overlap (the tile pre-stage is latency-bound on these loads: profiles/r01_v2 chain_f16_v3, two stall points).
+struct LutCell { const float* p; float fr, fg, fb; };
 
-VRGDG_HD void lut_pack_entry21(const float* cell24, uint32_t* dst16, int& bad) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t q[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = cell24[3 * k + c];
-      if (!(v >= 0.0f && v <= 1.0f)) bad = 1;
-      q[c] = (uint32_t)(clamp01(v) * LUT_Q21_SCALE + 0.5f);
-    }
-    dst16[2 * k] = q[0] | (q[1] << 21);
-    dst16[2 * k + 1] = (q[1] >> 11) | (q[2] << 10);
-  }
-}
-
-VRGDG_HD void lut_dec21(uint32_t w0, uint32_t w1, float& r, float& g, float& b) {
-  const uint32_t M = 0x1FFFFFu;
-#if defined(__CUDA_ARCH__)
-  const uint32_t C = 0x4B000000u;                      // as_float(C | k) - 2^23 == float(k) for k < 2^23: no I2F on the quarter-rate pipe
-  r = __uint_as_float((w0 & M) | C) - 8388608.0f;
-  g = __uint_as_float((__funnelshift_r(w0, w1, 21) & M) | C) - 8388608.0f;
-  b = __uint_as_float(((w1 >> 10) & M) | C) - 8388608.0f;
-#else
-  r = (float)(w0 & M);
-  g = (float)(((w0 >> 21) | (w1 << 11)) & M);
-  b = (float)((w1 >> 10) & M);
-#endif
-}
-
-VRGDG_HD void lut3d_eval21(const LutParams& P, float& r, float& g, float& b) {
+VRGDG_HD LutCell lut_locate(const LutParams& P, float r, float g, float b) {
   int r0, r1, g0, g1, b0, b1;
-  float fr, fg, fb;
-  lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
-  lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
-  lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
+  LutCell c;
+  lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, c.fr);
+  lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, c.fg);
+  lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, c.fb);
   (void)r1; (void)g1; (void)b1;
-  const float* p = reinterpret_cast<const float*>(P.q21 + (size_t)((b0 * P.S + g0) * P.S + r0) * 16);
-  const F8 lo = lut_load8(p), hi = lut_load8(p + 8);
-  float v[8][3];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-#if defined(__CUDA_ARCH__)
-    lut_dec21(__float_as_uint(lo.v[2 * k]), __float_as_uint(lo.v[2 * k + 1]), v[k][0], v[k][1], v[k][2]);
-    lut_dec21(__float_as_uint(hi.v[2 * k]), __float_as_uint(hi.v[2 * k + 1]), v[4 + k][0], v[4 + k][1], v[4 + k][2]);
-#else
-    uint32_t a0, a1, c0, c1;
-    memcpy(&a0, &lo.v[2 * k], 4); memcpy(&a1, &lo.v[2 * k + 1], 4); memcpy(&c0, &hi.v[2 * k], 4); memcpy(&c1, &hi.v[2 * k + 1], 4);
-    lut_dec21(a0, a1, v[k][0], v[k][1], v[k][2]);
-    lut_dec21(c0, c1, v[4 + k][0], v[4 + k][1], v[4 + k][2]);
-#endif
-  }
+  c.p = P.lut + (size_t)((b0 * P.S + g0) * P.S + r0) * LUT_CELL_FLOATS;
+  return c;
+}
+
+template <bool EXACT>
+VRGDG_HD void lut_finish(const LutCell& c, const F8& q0, const F8& q1, const F8& q2, float& r, float& g, float& b) {
+  const float v[24] = {q0.v[0], q0.v[1], q0.v[2], q0.v[3], q0.v[4], q0.v[5], q0.v[6], q0.v[7],
+                       q1.v[0], q1.v[1], q1.v[2], q1.v[3], q1.v[4], q1.v[5], q1.v[6], q1.v[7],
+                       q2.v[0], q2.v[1], q2.v[2], q2.v[3], q2.v[4], q2.v[5], q2.v[6], q2.v[7]};
+  const float omb = subx(1.0f, c.fb), omg = subx(1.0f, c.fg), omr = subx(1.0f, c.fr);
   float o[3];
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {       // corner order c000 c100 c010 c110 | c001 c101 c011 c111
-    const float c00 = fmaf(fb, v[4][ch] - v[0][ch], v[0][ch]), c10 = fmaf(fb, v[5][ch] - v[1][ch], v[1][ch]);
-    const float c01 = fmaf(fb, v[6][ch] - v[2][ch], v[2][ch]), c11 = fmaf(fb, v[7][ch] - v[3][ch], v[3][ch]);
-    const float c0 = fmaf(fg, c01 - c00, c00), c1 = fmaf(fg, c11 - c10, c10);
-    o[ch] = clamp01(fmaf(fr, c1 - c0, c0) * (1.0f / LUT_Q21_SCALE));
+  for (int ch = 0; ch < 3; ++ch) {
+    float c00 = lerp_ref<EXACT>(v[0 + ch], v[12 + ch], c.fb, omb);
+    float c01 = lerp_ref<EXACT>(v[6 + ch], v[18 + ch], c.fb, omb);
+    float c10 = lerp_ref<EXACT>(v[3 + ch], v[15 + ch], c.fb, omb);
+    float c11 = lerp_ref<EXACT>(v[9 + ch], v[21 + ch], c.fb, omb);
+    float c0 = lerp_ref<EXACT>(c00, c01, c.fg, omg);
+    float c1 = lerp_ref<EXACT>(c10, c11, c.fg, omg);
+    o[ch] = clamp01(lerp_ref<EXACT>(c0, c1, c.fr, omr));
   }
   r = o[0]; g = o[1]; b = o[2];
+}
+
+template <bool EXACT>
+VRGDG_HD void lut3d_eval2(const LutParams& P, float* a, float* b) {
+  const LutCell ca = lut_locate(P, a[0], a[1], a[2]), cb = lut_locate(P, b[0], b[1], b[2]);
+  const F8 a0 = lut_load8(ca.p), a1 = lut_load8(ca.p + 8), a2 = lut_load8(ca.p + 16);
+  const F8 b0 = lut_load8(cb.p), b1 = lut_load8(cb.p + 8), b2 = lut_load8(cb.p + 16);
+  lut_finish<EXACT>(ca, a0, a1, a2, a[0], a[1], a[2]);
+  lut_finish<EXACT>(cb, b0, b1, b2, b[0], b[1], b[2]);
 }
 
 // strength blend of apply_lut (:355-359) on already-rounded LUT output `y` and input `x`
@@ -501,6 +474,32 @@ VRGDG_HD float stencil_epilogue(int op, const float* n, float s) {
       v = c + s * sqrtf(m);
     } break;
     default: v = c;
+  }
+  return clamp01(v);
+}
+
+// Exact variants: the NumPy path's evaluation order with one rounding per operation -> bit-identical to the
+// reference's CPU sharpen nodes for fp32 frames (nodes.py:194-207, :278-287, :369-382).  The torch paths' convolutions
+// (F.conv2d) have no defined summation order; for them (ops 3 and 5) this falls back to the fast epilogue.
+VRGDG_HD float stencil_epilogue_exact(int op, const float* n, float s) {
+  const float c = n[4];
+  float v;
+  switch (op) {
+    case 1: {   // blur = (p00+p01+p02+p10+p11+p12+p20+p21+p22)/9.0, left to right ; out = img + s*(img - blur)
+      float sum = addx(addx(addx(addx(addx(addx(addx(addx(n[0], n[1]), n[2]), n[3]), n[4]), n[5]), n[6]), n[7]), n[8]);
+      float blur = divx(sum, 9.0f);
+      v = addx(c, mulx(s, subx(c, blur)));
+    } break;
+    case 2: {   // lap = W + N + S + E - 4.0*img ; out = img + s*lap
+      float lap = subx(addx(addx(addx(n[3], n[1]), n[7]), n[5]), mulx(4.0f, c));
+      v = addx(c, mulx(s, lap));
+    } break;
+    case 4: {   // gx = -p00 - 2*p10 - p20 + p02 + 2*p12 + p22 ; gy = -p00 - 2*p01 - p02 + p20 + 2*p21 + p22
+      float gx = addx(addx(addx(subx(subx(-n[0], mulx(2.0f, n[3])), n[6]), n[2]), mulx(2.0f, n[5])), n[8]);
+      float gy = addx(addx(addx(subx(subx(-n[0], mulx(2.0f, n[1])), n[2]), n[6]), mulx(2.0f, n[7])), n[8]);
+      v = addx(c, mulx(s, sqrtx(addx(mulx(gx, gx), mulx(gy, gy)))));
+    } break;
+    default: return stencil_epilogue(op, n, s);
   }
   return clamp01(v);
 }

@@ -88,9 +88,7 @@ VRGDG_API const char* vrgdg_last_tile_path(void);
 VRGDG_API int64_t vrgdg_lut3d_packed_bytes(int lut_size);
 /* lut: device [S,S,S,3] fp32 (reference layout); packed: device buffer of vrgdg_lut3d_packed_bytes(S), 32-byte aligned.
  * Entry (b,g,r) of the packed table = the 8 corners of the cell whose origin is (b,g,r) (neighbours clamped to S-1), 24 floats
- * = 96 bytes: a pixel's whole trilinear stencil arrives with three consecutive 256-bit loads.  The buffer also holds a
- * 64-byte-per-cell unorm21 copy (two loads per pixel, |error| <= 2.4e-7) that only the tolerance-checked fused chains with
- * in-kernel noise use, and only when every table value lies in [0,1]; the LUT entry point always reads the fp32 cells. */
+ * = 96 bytes: a pixel's whole trilinear stencil arrives with three consecutive 256-bit loads. */
 VRGDG_API int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream);
 VRGDG_API int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int dtype,
                       const float* lut_packed, int lut_size,

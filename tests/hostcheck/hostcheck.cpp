@@ -53,11 +53,8 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
   float* packed = new float[(size_t)S * S * S * LUT_CELL_FLOATS];
   for (int bb = 0; bb < S; ++bb) for (int gg = 0; gg < S; ++gg) for (int rr = 0; rr < S; ++rr)
     lut_pack_entry(lut, S, bb, gg, rr, packed + ((size_t)(bb * S + gg) * S + rr) * LUT_CELL_FLOATS);
-  uint32_t* q21 = new uint32_t[(size_t)S * S * S * 16];
-  int bad = 0;
-  for (size_t c = 0; c < (size_t)S * S * S; ++c) lut_pack_entry21(packed + c * LUT_CELL_FLOATS, q21 + c * 16, bad);
   LutParams P;
-  P.lut = packed; P.q21 = q21; P.q21_bad = &bad; P.S = S; P.smax = (float)(S - 1);
+  P.lut = packed; P.S = S; P.smax = (float)(S - 1);
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
   P.blend = blend; P.one_minus_blend = omb;
   P.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f);
@@ -65,8 +62,11 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
     float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
     float x0 = r, x1 = g, x2 = b;
     if (exact == 1) lut3d_eval<true>(P, r, g, b);
-    else if (exact == 2 && bad == 0) lut3d_eval21(P, r, g, b);       // unorm21 fast table
-    else lut3d_eval<false>(P, r, g, b);
+    else if (exact == 2) {                                           // the two-pixel form the kernels use (pixel paired with itself)
+      float a[3] = {r, g, b}, c[3] = {r, g, b};
+      lut3d_eval2<true>(P, a, c);
+      r = c[0]; g = a[1]; b = c[2];
+    } else lut3d_eval<false>(P, r, g, b);
     if (blend < 1.0f) {
       if (exact) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }
       else { r = lut_blend<false>(x0, r, blend, omb); g = lut_blend<false>(x1, g, blend, omb); b = lut_blend<false>(x2, b, blend, omb); }
@@ -74,7 +74,6 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
     out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
   }
   delete[] packed;
-  delete[] q21;
 }
 
 void hc_rgb_to_lab(const float* in, float* out, int64_t n) {
@@ -94,7 +93,7 @@ void hc_colormatch(const float* in, float* out, int64_t n, const float* params, 
 }
 
 // frames [H][W][3], border 0 replicate / 1 zero
-void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int border) {
+void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int border, int exact) {
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x)
       for (int c = 0; c < 3; ++c) {
@@ -112,7 +111,7 @@ void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int 
             }
             n9[(dy + 1) * 3 + dx + 1] = v;
           }
-        out[(y * W + x) * 3 + c] = stencil_epilogue(op, n9, s);
+        out[(y * W + x) * 3 + c] = exact ? stencil_epilogue_exact(op, n9, s) : stencil_epilogue(op, n9, s);
       }
 }
 

@@ -474,32 +474,3 @@ def test_full_chain_with_colormatch_partition_invariance(pkg, cuda_device):
     c = pkg.ops.lut3d_apply(b, lut["lut"], [0, 0, 0], [1, 1, 1], 1.0, 0.0)
     d = pkg.ops.stencil3x3(c, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
     assert maxdiff(whole, d) <= 5e-6
-
-
-def test_fast_chain_unorm21_table_and_out_of_range_fallback(pkg, cuda_device):
-    """Fused chains with in-kernel noise read the unorm21 cell table (2 lookups/px) when every LUT value is in [0,1];
-    otherwise the fp32 cell table.  Both must agree with the exact-table chain to 1e-6."""
-    nv = pkg._native
-    x = natural_frames(2, 136, 248, seed=12, device=cuda_device)
-    lut = _lut33(pkg)
-    mk = lambda data: pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=7), lut=dict(lut_data=data, strength=8.0),
-                                          stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
-    fast = mk(lut)(x)
-    os.environ["VRGDG_NO_Q21"] = "1"
-    try:
-        fp32_cells = mk(lut)(x)
-    finally:
-        del os.environ["VRGDG_NO_Q21"]
-    assert maxdiff(fast, fp32_cells) <= 1e-6 and not torch.equal(fast, fp32_cells)      # really a different table
-    # a table with values outside [0,1] must not be quantised: results identical with and without the switch
-    wild = dict(lut, lut=(lut["lut"] * 1.3 - 0.1))
-    a = mk(wild)(x)
-    os.environ["VRGDG_NO_Q21"] = "1"
-    try:
-        b = mk(wild)(x)
-    finally:
-        del os.environ["VRGDG_NO_Q21"]
-    assert torch.equal(a, b)
-    ref = pkg.ops.stencil3x3(pkg.ops.lut3d_apply(pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=7), wild["lut"], [0, 0, 0], [1, 1, 1], 0.8, 1.0 - 0.8),
-                             nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
-    assert maxdiff(a, ref) <= 2e-6

@@ -99,19 +99,28 @@ def test_lut_eval_exact_is_bit_identical(hostcheck, oracle):
         assert np.array_equal(o, flat(g[f"{key}__s3p5"])), fname
         hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 0)      # contracted variant
         assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
-        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 2)      # unorm21 fast table
-        assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 2)      # two-pixel form
+        assert np.array_equal(o, flat(g[f"{key}__s10"])), fname
 
 
 def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
-    hostcheck.hc_stencil.argtypes = [vp, vp, ci, ci, ci, f32, ci]
+    hostcheck.hc_stencil.argtypes = [vp, vp, ci, ci, ci, f32, ci, ci]
     g = load_golden("stencil")
     x = np.ascontiguousarray(g["x"][0])
     o = np.zeros_like(x)
     for op, key, border in ((1, "unsharp_np", 0), (1, "unsharp_torch", 1), (2, "laplacian_np", 0), (3, "laplacian_torch", 1),
                             (4, "sobel_np", 0), (5, "sobel_torch", 1)):
-        hostcheck.hc_stencil(P(x), P(o), x.shape[0], x.shape[1], op, 0.5, border)
+        hostcheck.hc_stencil(P(x), P(o), x.shape[0], x.shape[1], op, 0.5, border, 0)
         assert np.abs(o - g[key][0]).max() <= 1e-5, key
+    # exact epilogues: bit-identical to the NumPy paths (and to avg_pool2d for the zero-padded unsharp)
+    for op, key, border, s in ((1, "unsharp_np", 0, 0.5), (2, "laplacian_np", 0, 0.5), (4, "sobel_np", 0, 0.5), (1, "unsharp_torch", 1, 0.5), (1, "unsharp_np_s10", 0, 10.0)):
+        hostcheck.hc_stencil(P(x), P(o), x.shape[0], x.shape[1], op, s, border, 1)
+        assert np.array_equal(o, g[key][0]), key
+    xo = np.ascontiguousarray(g["x_odd"][0])
+    oo = np.zeros_like(xo)
+    for op, key in ((1, "unsharp_np_odd"), (2, "laplacian_np_odd"), (4, "sobel_np_odd")):
+        hostcheck.hc_stencil(P(xo), P(oo), xo.shape[0], xo.shape[1], op, 1.3, 0, 1)
+        assert np.array_equal(oo, g[key][0]), key
     hostcheck.hc_colormatch.argtypes = [vp, vp, i64, vp, f32, f32]
     c = load_golden("colormatch")
     ref_s = oracle.lab_moments_f64(t(c["ref"]))[0].numpy()
