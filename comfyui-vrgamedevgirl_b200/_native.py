@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvrgdg_b200.so")
 VRGDG_OK = 0
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN = -1, -2, -3, -4
 
-F32, F16, BF16 = 0, 1, 2
-DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+F32, F16, BF16, U8BGR = 0, 1, 2, 3
+DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16, torch.uint8: U8BGR}
 
 STENCIL_NONE, STENCIL_BOX_UNSHARP, STENCIL_LAPLACIAN_CPU, STENCIL_LAPLACIAN_GPU, STENCIL_SOBEL_CPU, STENCIL_SOBEL_GPU = range(6)
 BORDER_REPLICATE, BORDER_ZERO = 0, 1
@@ -130,7 +130,7 @@ def require_cuda(t, name="tensor"):
     if t.device.type != "cuda":
         raise RuntimeError("vrgdg_b200: %s must live on a CUDA device (got %s); the filters have no CPU path" % (name, t.device))
     if t.dtype not in DTYPE_CODE:
-        raise ValueError("vrgdg_b200: unsupported dtype %s (float32 / float16 / bfloat16)" % t.dtype)
+        raise ValueError("vrgdg_b200: unsupported dtype %s (float32 / float16 / bfloat16 / uint8 BGR)" % t.dtype)
     return t if t.is_contiguous() else t.contiguous()
 
 

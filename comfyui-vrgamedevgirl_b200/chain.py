@@ -53,8 +53,9 @@ class PostChain:
             data = self.lut["lut_data"]
             blend = max(0.0, min(10.0, float(self.lut.get("strength", 10.0)))) / 10.0
             if blend > 0.0:
-                dmin = data["domain_min"].to(dtype=frames.dtype)
-                span = torch.clamp(data["domain_max"].to(dtype=frames.dtype) - dmin, min=1e-6)
+                fdt = torch.float32 if frames.dtype == torch.uint8 else frames.dtype     # uint8 frames become float32 tensors in the reference
+                dmin = data["domain_min"].to(dtype=fdt)
+                span = torch.clamp(data["domain_max"].to(dtype=fdt) - dmin, min=1e-6)
                 d.lut_enabled = 1
                 d.lut = self._lut_dev.data.data_ptr()
                 d.lut_size = self._lut_dev.size

@@ -31,8 +31,8 @@ int fail_cuda(cudaError_t e, const char* where) {
   return fail(VRGDG_E_CUDA, "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-size_t elem_size(int dtype) { return dtype == VRGDG_F32 ? 4 : 2; }
-bool dtype_ok(int dtype) { return dtype == VRGDG_F32 || dtype == VRGDG_F16 || dtype == VRGDG_BF16; }
+size_t elem_size(int dtype) { return dtype == VRGDG_F32 ? 4 : (dtype == VRGDG_U8BGR ? 1 : 2); }
+bool dtype_ok(int dtype) { return dtype == VRGDG_F32 || dtype == VRGDG_F16 || dtype == VRGDG_BF16 || dtype == VRGDG_U8BGR; }
 
 int get_ctx(void* stream, LaunchCtx& ctx) {
   int dev = 0;
@@ -65,7 +65,7 @@ int check_frames(const void* in, const void* out, int B, int H, int W, int dtype
 }
 
 #define DISPATCH_DTYPE(dtype, CALL)                                        \
-  ((dtype) == VRGDG_F32 ? CALL(float) : ((dtype) == VRGDG_F16 ? CALL(__half) : CALL(__nv_bfloat16)))
+  ((dtype) == VRGDG_F32 ? CALL(float) : ((dtype) == VRGDG_F16 ? CALL(__half) : ((dtype) == VRGDG_BF16 ? CALL(__nv_bfloat16) : CALL(uint8_t))))
 
 // ---- TMA tensor map over frames [B][H][RW] ---------------------------------------------------------
 typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -93,7 +93,8 @@ bool build_tmap(CUtensorMap* map, const void* in, int B, int H, int RW, int dtyp
   encode_fn_t enc = get_encode();
   if (!enc) return false;
   CUtensorMapDataType dt = dtype == VRGDG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                         : dtype == VRGDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+                         : dtype == VRGDG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                         : dtype == VRGDG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   cuuint64_t dims[3] = {(cuuint64_t)RW, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)RW * es, (cuuint64_t)RW * es * (cuuint64_t)H};
   cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
@@ -201,6 +202,7 @@ int vrgdg_lut3d_apply(const void* in, void* out, int64_t npix, int channels, int
   LutParams L;
   fill_lut(L, lut, lut_size, dmin_host, dspan_host, blend, one_minus_blend);
   cudaError_t e;
+  if (channels == 4 && dtype == VRGDG_U8BGR) return fail(VRGDG_E_UNSUPPORTED, "vrgdg_lut3d_apply: 4-channel uint8 frames are not supported");
   if (channels == 4) {
 #define LR(T) launch_lut_rgba<T>(in, out, npix, L, ctx)
     e = DISPATCH_DTYPE(dtype, LR);
@@ -278,7 +280,7 @@ int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, int dtype, 
   memset(&Q, 0, sizeof(Q));
   zero_point(Q.P, B, H, W);
   Q.op = op; Q.strength = strength; Q.border = border;
-  Q.exact_stencil = (dtype == VRGDG_F32) ? 1 : 0;     // fp32 frames: bit-identical to the NumPy nodes; 16-bit frames round once anyway
+  Q.exact_stencil = (dtype == VRGDG_F32 || dtype == VRGDG_U8BGR) ? 1 : 0;   // fp32 / byte frames: bit-identical to the NumPy nodes; 16-bit frames round once anyway
   return run_tile(in, out, B, H, W, dtype, Q, 0, true, ctx);
 }
 
@@ -408,7 +410,7 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
     return VRGDG_OK;
   }
   Q.op = d->stencil_op; Q.strength = d->stencil_strength; Q.border = d->stencil_border;
-  Q.exact_stencil = (exact && dtype == VRGDG_F32) ? 1 : 0;
+  Q.exact_stencil = (exact && (dtype == VRGDG_F32 || dtype == VRGDG_U8BGR)) ? 1 : 0;
   Q.post_enabled = d->post_grain_enabled ? 1 : 0;
   Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
   Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;
@@ -443,7 +445,7 @@ int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, cons
 }
 
 int vrgdg_u8bgr_to_rgb(const uint8_t* in, void* out, int64_t npix, int dtype, void* stream) {
-  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: unknown dtype %d", dtype);
+  if (!dtype_ok(dtype) || dtype == VRGDG_U8BGR) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: float dtype expected, got %d", dtype);
   if (npix < 0) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: negative pixel count");
   if (npix == 0) return VRGDG_OK;
   if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_u8bgr_to_rgb: null pointer");
@@ -451,14 +453,14 @@ int vrgdg_u8bgr_to_rgb(const uint8_t* in, void* out, int64_t npix, int dtype, vo
   int rc = get_ctx(stream, ctx);
   if (rc) return rc;
 #define UI(T) launch_u8_in<T>(in, out, npix, ctx)
-  cudaError_t e = DISPATCH_DTYPE(dtype, UI);
+  cudaError_t e = (dtype == VRGDG_F32) ? UI(float) : ((dtype == VRGDG_F16) ? UI(__half) : UI(__nv_bfloat16));
 #undef UI
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_u8bgr_to_rgb");
   return VRGDG_OK;
 }
 
 int vrgdg_rgb_to_u8bgr(const void* in, uint8_t* out, int64_t npix, int dtype, void* stream) {
-  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: unknown dtype %d", dtype);
+  if (!dtype_ok(dtype) || dtype == VRGDG_U8BGR) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: float dtype expected, got %d", dtype);
   if (npix < 0) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: negative pixel count");
   if (npix == 0) return VRGDG_OK;
   if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_rgb_to_u8bgr: null pointer");
@@ -466,7 +468,7 @@ int vrgdg_rgb_to_u8bgr(const void* in, uint8_t* out, int64_t npix, int dtype, vo
   int rc = get_ctx(stream, ctx);
   if (rc) return rc;
 #define UO(T) launch_u8_out<T>(in, out, npix, ctx)
-  cudaError_t e = DISPATCH_DTYPE(dtype, UO);
+  cudaError_t e = (dtype == VRGDG_F32) ? UO(float) : ((dtype == VRGDG_F16) ? UO(__half) : UO(__nv_bfloat16));
 #undef UO
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_rgb_to_u8bgr");
   return VRGDG_OK;

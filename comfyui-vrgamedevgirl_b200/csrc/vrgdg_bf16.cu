@@ -2,4 +2,5 @@
 #include "vrgdg_inst.cuh"
 namespace vrgdg {
 VRGDG_INSTANTIATE(__nv_bfloat16)
+VRGDG_INSTANTIATE_CODECS(__nv_bfloat16)
 }

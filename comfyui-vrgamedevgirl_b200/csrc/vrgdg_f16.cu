@@ -2,4 +2,5 @@
 #include "vrgdg_inst.cuh"
 namespace vrgdg {
 VRGDG_INSTANTIATE(__half)
+VRGDG_INSTANTIATE_CODECS(__half)
 }

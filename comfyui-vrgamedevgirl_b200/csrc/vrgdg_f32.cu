@@ -2,4 +2,5 @@
 #include "vrgdg_inst.cuh"
 namespace vrgdg {
 VRGDG_INSTANTIATE(float)
+VRGDG_INSTANTIATE_CODECS(float)
 }

@@ -18,7 +18,7 @@ static int occupancy_of(K kernel, int threads, size_t smem) {
 // ---- k_point ---------------------------------------------------------------------------------
 template <typename T, int MASK, bool EXACT, bool VEC>
 static cudaError_t launch_point_k(const void* in, void* out, const PointParams& P, const LaunchCtx& ctx) {
-  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;
+  constexpr int PX = VEC ? (int)(3 * sizeof(typename Io<T>::word_t) / (3 * sizeof(T))) : 1;
   const int64_t groups = (P.hw + PX - 1) / PX;
   const int bpf = (int)((groups + 255) / 256);
   const int64_t total = (int64_t)bpf * P.B;
@@ -35,8 +35,10 @@ static cudaError_t launch_point_k(const void* in, void* out, const PointParams& 
 
 template <typename T, int MASK, bool EXACT>
 static cudaError_t launch_point_v(const void* in, void* out, const PointParams& P, const LaunchCtx& ctx) {
-  constexpr int PX = (int)(48 / (3 * sizeof(T)));
-  bool vec = (P.hw % PX == 0) && (P.W % PX == 0) && aligned16(in) && aligned16(out) &&
+  typedef typename Io<T>::word_t word_t;
+  constexpr int PX = (int)(3 * sizeof(word_t) / (3 * sizeof(T)));
+  auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & (sizeof(word_t) - 1)) == 0; };
+  bool vec = (P.hw % PX == 0) && (P.W % PX == 0) && ok(in) && ok(out) &&
              (!(MASK & ST_GRAIN) || P.ext_noise == nullptr || aligned16(P.ext_noise));
   if (vec) return launch_point_k<T, MASK, EXACT, true>(in, out, P, ctx);
   return launch_point_k<T, MASK, EXACT, false>(in, out, P, ctx);
@@ -147,8 +149,10 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_lut_rgba<T>(const void*, void*, int64_t, const LutParams&, const LaunchCtx&);               \
   template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
   template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&); \
-  template cudaError_t launch_u8_in<T>(const uint8_t*, void*, int64_t, const LaunchCtx&);                                 \
-  template cudaError_t launch_u8_out<T>(const void*, uint8_t*, int64_t, const LaunchCtx&);                                \
   template void tile_geometry<T>(int, int, int&, int&, int&, int&);
+
+#define VRGDG_INSTANTIATE_CODECS(T)                                                                                       \
+  template cudaError_t launch_u8_in<T>(const uint8_t*, void*, int64_t, const LaunchCtx&);                                 \
+  template cudaError_t launch_u8_out<T>(const void*, uint8_t*, int64_t, const LaunchCtx&);
 
 }  // namespace vrgdg

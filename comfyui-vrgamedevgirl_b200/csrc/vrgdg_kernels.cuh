@@ -32,6 +32,26 @@ template <> struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ __nv_bfloat16 st(float v) { return __float2bfloat16_rn(v); }
 };
 
+// uint8 frames are the reference's video wire format (cv2 BGR bytes): x/255.0 on the way in, clip(x*255,0,255) TRUNCATED on
+// the way out (VRGDG_LUTVideoTools.py:736-752), channel order swapped to RGB inside the kernels.
+template <> struct Elem<uint8_t> {
+  static __device__ __forceinline__ float ld(uint8_t v) { return divx((float)v, 255.0f); }
+  static __device__ __forceinline__ uint8_t st(float v) { return (uint8_t)fminf(fmaxf(mulx(v, 255.0f), 0.0f), 255.0f); }
+};
+
+template <typename T> struct Io {
+  static constexpr bool BGR = false;          // memory order of a pixel's channels
+  typedef T noise_t;                          // element type of an external noise tensor
+  typedef uint4 word_t;                       // a thread moves 3 words = whole pixels
+};
+template <> struct Io<uint8_t> {
+  static constexpr bool BGR = true;
+  typedef float noise_t;
+  typedef uint32_t word_t;
+};
+template <typename T> __device__ __forceinline__ float noise_ld(T v) { return Elem<T>::ld(v); }
+template <> __device__ __forceinline__ float noise_ld<float>(float v) { return v; }
+
 // ---- parameters of the per-pixel stages ------------------------------------------------------------
 struct PointParams {
   int B, H, W;
@@ -96,7 +116,10 @@ template <typename T, int MASK, bool EXACT, bool VEC>
 __global__ void __launch_bounds__(256)
 k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         int blocks_per_frame, int64_t total_vblocks) {
-  constexpr int PX = VEC ? (int)(48 / (3 * sizeof(T))) : 1;   // VEC additionally requires W % PX == 0 (a group never wraps a row)
+  typedef typename Io<T>::word_t word_t;
+  typedef typename Io<T>::noise_t noise_t;
+  constexpr bool BGR = Io<T>::BGR;
+  constexpr int PX = VEC ? (int)(3 * sizeof(word_t) / (3 * sizeof(T))) : 1;   // 4 fp32 / 8 fp16 / 4 u8 pixels; VEC needs W % PX == 0
   constexpr int NE = PX * 3;
   constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
   const bool has_ext = GRAIN && (P.ext_noise != nullptr);
@@ -111,28 +134,32 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
     const uint32_t y = GRAIN ? (uint32_t)pix0 / (uint32_t)P.W : 0u;
     const uint32_t x = GRAIN ? (uint32_t)pix0 - y * (uint32_t)P.W : 0u;
 
-    float v[NE];
+    float v[NE];     // RGB order
     float nz[NE];
+    union { word_t q[3]; T e[NE]; } u;
     if (VEC) {
-      union { uint4 q[3]; T e[NE]; } u;
-      const uint4* src = reinterpret_cast<const uint4*>(in + e0);
+      const word_t* src = reinterpret_cast<const word_t*>(in + e0);
       u.q[0] = __ldg(src); u.q[1] = __ldg(src + 1); u.q[2] = __ldg(src + 2);
-#pragma unroll
-      for (int i = 0; i < NE; ++i) v[i] = Elem<T>::ld(u.e[i]);
-      if (has_ext) {
-        union { uint4 q[3]; T e[NE]; } n;
-        const uint4* ns = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(P.ext_noise) + e0);
-        n.q[0] = __ldg(ns); n.q[1] = __ldg(ns + 1); n.q[2] = __ldg(ns + 2);
-#pragma unroll
-        for (int i = 0; i < NE; ++i) nz[i] = Elem<T>::ld(n.e[i]);
-      }
     } else {
 #pragma unroll
-      for (int i = 0; i < NE; ++i) v[i] = Elem<T>::ld(in[e0 + i]);
-      if (has_ext) {
-        const T* ns = reinterpret_cast<const T*>(P.ext_noise) + e0;
+      for (int i = 0; i < NE; ++i) u.e[i] = in[e0 + i];
+    }
 #pragma unroll
-        for (int i = 0; i < NE; ++i) nz[i] = Elem<T>::ld(ns[i]);
+    for (int j = 0; j < PX; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 * j + c] = Elem<T>::ld(u.e[3 * j + (BGR ? 2 - c : c)]);
+    }
+    if (has_ext) {   // external noise is [B,H,W,3] in RGB order (test path)
+      const noise_t* ns = reinterpret_cast<const noise_t*>(P.ext_noise) + e0;
+      if (VEC && sizeof(noise_t) == sizeof(T)) {
+        union { word_t q[3]; noise_t e[NE]; } n;
+        const word_t* nq = reinterpret_cast<const word_t*>(ns);
+        n.q[0] = __ldg(nq); n.q[1] = __ldg(nq + 1); n.q[2] = __ldg(nq + 2);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nz[i] = noise_ld<noise_t>(n.e[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nz[i] = noise_ld<noise_t>(ns[i]);
       }
     }
     if (VEC) {
@@ -150,11 +177,6 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         }
         process_pair<MASK, EXACT>(P, cmp, z, &v[3 * j]);
       }
-      union { uint4 q[3]; T e[NE]; } u;
-#pragma unroll
-      for (int i = 0; i < NE; ++i) u.e[i] = Elem<T>::st(v[i]);
-      uint4* dst = reinterpret_cast<uint4*>(out + e0);
-      dst[0] = u.q[0]; dst[1] = u.q[1]; dst[2] = u.q[2];
     } else {
       float zr = 0.f, zg = 0.f, zb = 0.f;
       if (GRAIN) {
@@ -162,8 +184,18 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         else grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
       }
       process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2]);
+    }
 #pragma unroll
-      for (int i = 0; i < NE; ++i) out[e0 + i] = Elem<T>::st(v[i]);
+    for (int j = 0; j < PX; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u.e[3 * j + (BGR ? 2 - c : c)] = Elem<T>::st(v[3 * j + c]);
+    }
+    if (VEC) {
+      word_t* dst = reinterpret_cast<word_t*>(out + e0);
+      dst[0] = u.q[0]; dst[1] = u.q[1]; dst[2] = u.q[2];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) out[e0 + i] = u.e[i];
     }
   }
 }
@@ -268,10 +300,10 @@ struct TileParams {
 // 4 elements per row (16-byte shared loads at a 16-byte lane stride are bank-conflict free; 32-byte strides are not).
 template <typename T, int MASK> struct TileCfg {
   static constexpr bool HEAVY = (MASK & ST_LUT) != 0;
-  static constexpr bool WORK = (MASK != 0) && (sizeof(T) != 4);
+  static constexpr bool WORK = (sizeof(T) == 1) || ((MASK != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
   static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
-  static constexpr int PADL = 16 / (int)sizeof(T);    // box starts PADL elements left of the tile (>= 3, keeps 16-byte alignment)
+  static constexpr int PADL = sizeof(T) == 1 ? 4 : 16 / (int)sizeof(T);   // box starts PADL elements left of the tile (>= 3, even)
   static constexpr int TXE = 240;                     // output elements per tile row (multiple of 6 and of VEC)
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
@@ -348,7 +380,7 @@ __device__ __forceinline__ void load_window(const E* rowp /* -> tile column PADL
 }
 
 // grain after the stencil (EnhancerNodes.py:285-293) on VEC consecutive row elements starting at element ge0
-template <int VEC>
+template <int VEC, bool BGR>
 __device__ __forceinline__ void post_grain_elems(const TileParams& Q, const GrainFrame& gf, int ge0, int y, float* o) {
   const int pfirst = ge0 / 3, plast = (ge0 + VEC - 1) / 3;
   constexpr int NPR = (VEC + 1) / 3 + 1;                    // pixel pairs a run of VEC elements can touch
@@ -363,9 +395,11 @@ __device__ __forceinline__ void post_grain_elems(const TileParams& Q, const Grai
     const float g3 = fmaf(2.0f * Q.ps, z[3], gy1), g4 = fmaf(Q.ps, z[4], gy1), g5 = fmaf(3.0f * Q.ps, z[5], gy1);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const int idx = ge0 + e - pair * 6;                   // 0..5 inside this pair
+      const int idx = ge0 + e - pair * 6;                   // 0..5 inside this pair (memory order)
       if (idx >= 0 && idx < 6) {
-        const float gv = (idx < 3) ? ((idx == 0) ? g0 : ((idx == 1) ? g1 : g2)) : ((idx == 3) ? g3 : ((idx == 4) ? g4 : g5));
+        const float lo = (idx == 0) ? (BGR ? g2 : g0) : ((idx == 1) ? g1 : (BGR ? g0 : g2));
+        const float hi = (idx == 3) ? (BGR ? g5 : g3) : ((idx == 4) ? g4 : (BGR ? g3 : g5));
+        const float gv = (idx < 3) ? lo : hi;
         o[e] = clamp01(fmaf(Q.pI, gv, o[e]));
       }
     }
@@ -382,11 +416,16 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
 #pragma unroll
         for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
         *reinterpret_cast<uint4*>(dst) = u.q;
-      } else {
+      } else if (VEC * sizeof(T) == 8) {
         union { uint2 q; T e[VEC]; } u;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
         *reinterpret_cast<uint2*>(dst) = u.q;
+      } else {
+        union { uint32_t q; T e[VEC]; } u;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) u.e[e] = Elem<T>::st(o[e]);
+        *reinterpret_cast<uint32_t*>(dst) = u.q;
       }
     } else {
 #pragma unroll
@@ -408,7 +447,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
   const int ge0 = x0e + f0;                 // first output element in the row
   const int rbase = rg * C::RPT;            // first output row of this thread == smem row of its upper neighbour
   auto load_row = [&](int srow, float* dst) {
-    if (WORK) load_window<float, VEC>(work + srow * BX + PADL + f0, dst);
+    if constexpr (WORK) load_window<float, VEC>(work + srow * BX + PADL + f0, dst);
     else load_window<T, VEC>(raw + srow * BX + PADL + f0, dst);
   };
   const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
@@ -433,7 +472,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
         o[e] = clamp01(fmaf(Q.strength, c1[e] - blur, c1[e]));                 // img + s*(img - blur)
         h0[e] = h1[e]; h1[e] = h2; c1[e] = wr[e + 3];
       }
-      if (Q.post_enabled) post_grain_elems<VEC>(Q, pgf, ge0, y, o);
+      if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
     }
   } else {
@@ -451,7 +490,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
                       w[2][e], w[2][e + 3], w[2][e + 6]};
         o[e] = XS ? stencil_epilogue_exact(OP, n, Q.strength) : stencil_epilogue(OP, n, Q.strength);
       }
-      if (Q.post_enabled) post_grain_elems<VEC>(Q, pgf, ge0, y, o);
+      if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
 #pragma unroll
       for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
@@ -467,10 +506,16 @@ __device__ __forceinline__ void pair_load6(const T* p, bool word0, float* e) {
     if (word0) { float2 v = q[0]; e[0] = v.x; e[1] = v.y; }
     float2 v1 = q[1], v2 = q[2];
     e[2] = v1.x; e[3] = v1.y; e[4] = v2.x; e[5] = v2.y;
-  } else {
+  } else if (sizeof(T) == 2) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
     union { uint32_t u[3]; T h[6]; } w;
     w.u[0] = word0 ? q[0] : 0u; w.u[1] = q[1]; w.u[2] = q[2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e[i] = Elem<T>::ld(w.h[i]);
+  } else {
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    union { uint16_t u[3]; T h[6]; } w;
+    w.u[0] = word0 ? q[0] : (uint16_t)0; w.u[1] = q[1]; w.u[2] = q[2];
 #pragma unroll
     for (int i = 0; i < 6; ++i) e[i] = Elem<T>::ld(w.h[i]);
   }
@@ -562,9 +607,11 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
 
     // ---- per-pixel pre-stages over the halo tile (grain / colour match / LUT), result in fp32 ----
     // one task = one generator pixel pair (2 horizontally adjacent pixels): one Philox call, two independent LUT gathers in flight
-    if (MASK != 0) {
+    if (MASK != 0 || WORK) {
       const PointParams& P = Q.P;
       constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
+      constexpr bool BGR = Io<T>::BGR;
+      typedef typename Io<T>::noise_t noise_t;
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
@@ -586,31 +633,31 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
           float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (GRAIN) {
             if (has_ext) {
-              const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + (int64_t)y * Q.W + pxa) * 3;
-              if (in_a) { z[0] = Elem<T>::ld(ns[0]); z[1] = Elem<T>::ld(ns[1]); z[2] = Elem<T>::ld(ns[2]); }
-              if (in_b) { z[3] = Elem<T>::ld(ns[3]); z[4] = Elem<T>::ld(ns[4]); z[5] = Elem<T>::ld(ns[5]); }
+              const noise_t* ns = reinterpret_cast<const noise_t*>(P.ext_noise) + ((int64_t)frame * P.hw + (int64_t)y * Q.W + pxa) * 3;
+              if (in_a) { z[0] = noise_ld<noise_t>(ns[0]); z[1] = noise_ld<noise_t>(ns[1]); z[2] = noise_ld<noise_t>(ns[2]); }
+              if (in_b) { z[3] = noise_ld<noise_t>(ns[3]); z[4] = noise_ld<noise_t>(ns[4]); z[5] = noise_ld<noise_t>(ns[5]); }
             } else {
               grain_pair_normals(grain_pair_bits(P.gkey, gf, (uint32_t)pair, (uint32_t)y), z);
             }
           }
           // both pixels go through the stages unconditionally (their 2 x 3 LUT loads are then in flight together; a pixel
           // outside the image computes on staged zeros and is discarded) - the branchy form serialised the two gathers
-          float p[6] = {e[0], e[1], e[2], e[3], e[4], e[5]};
+          float p[6] = {e[BGR ? 2 : 0], e[1], e[BGR ? 0 : 2], e[BGR ? 5 : 3], e[4], e[BGR ? 3 : 5]};     // RGB for the stages
           process_pair<MASK, EXACT>(P, cmp, z, p);
-          if (in_a) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; } else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
-          if (in_b) { e[3] = p[3]; e[4] = p[4]; e[5] = p[5]; } else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
+          if (in_a) { e[BGR ? 2 : 0] = p[0]; e[1] = p[1]; e[BGR ? 0 : 2] = p[2]; } else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
+          if (in_b) { e[BGR ? 5 : 3] = p[3]; e[4] = p[4]; e[BGR ? 3 : 5] = p[5]; } else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
-        if (WORK) {
-          pair_store6(work + so, kx > 0, e);                       // zeros for pixels outside the image
-        } else if (in_a | in_b) {
-          pair_store6(reinterpret_cast<float*>(raw) + so, kx > 0, e);   // in place; untouched pixels keep their staged value
+        if constexpr (WORK) {
+          pair_store6(work + so, kx > 0, e);                       // zeros for pixels outside the image (memory channel order kept)
+        } else {
+          if (in_a | in_b) pair_store6(reinterpret_cast<float*>(raw) + so, kx > 0, e);   // in place; untouched pixels keep their staged value
         }
       }
       __syncthreads();
     }
 
     if (Q.border == 0) {
-      if (WORK) fix_border<float, C>(work, y0, x0e, Q.H, Q.RW);
+      if constexpr (WORK) fix_border<float, C>(work, y0, x0e, Q.H, Q.RW);
       else fix_border<T, C>(raw, y0, x0e, Q.H, Q.RW);
     }
 
@@ -666,12 +713,13 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     int64_t pif = pbeg + i;
     const T* s = fbase + pif * 3;
-    float r = Elem<T>::ld(s[0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[2]);
+    float r = Elem<T>::ld(s[Io<T>::BGR ? 2 : 0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[Io<T>::BGR ? 0 : 2]);
     if (GRAIN) {
       float nr = 0.f, ng = 0.f, nb = 0.f;
       if (has_ext) {
-        const T* ns = reinterpret_cast<const T*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
-        nr = Elem<T>::ld(ns[0]); ng = Elem<T>::ld(ns[1]); nb = Elem<T>::ld(ns[2]);
+        typedef typename Io<T>::noise_t noise_t;
+        const noise_t* ns = reinterpret_cast<const noise_t*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
+        nr = noise_ld<noise_t>(ns[0]); ng = noise_ld<noise_t>(ns[1]); nb = noise_ld<noise_t>(ns[2]);
         process_pixel<ST_GRAIN, true>(P, nullptr, nr, ng, nb, r, g, b);
       } else {
         const uint32_t y = (uint32_t)pif / (uint32_t)P.W, x = (uint32_t)pif - y * (uint32_t)P.W;

@@ -18,6 +18,15 @@ def _f32(v):
     return ctypes.c_float(float(v))
 
 
+def _noise(ext_noise, frames):
+    """external N(0,1) tensor: same shape/device as the frames, same dtype (float32 for uint8 frames), RGB order"""
+    n = nv.require_cuda(ext_noise, "ext_noise")
+    want = torch.float32 if frames.dtype == torch.uint8 else frames.dtype
+    if n.shape != frames.shape or n.dtype != want or n.device != frames.device:
+        raise ValueError("vrgdg_b200: ext_noise must match images in shape and device, dtype %s" % want)
+    return n
+
+
 class PackedLut:
     """A 3D LUT in the library's device layout (vrgdg_lut3d_pack): `data` float32 [S^3 * 24] on a CUDA device."""
 
@@ -70,9 +79,7 @@ def grain(images, intensity, sat, one_minus_sat, seed, frame0=0, seed_mode=nv.SE
     t = _frames(images)
     n = None
     if ext_noise is not None:
-        n = nv.require_cuda(ext_noise, "ext_noise")
-        if n.shape != t.shape or n.dtype != t.dtype or n.device != t.device:
-            raise ValueError("vrgdg_b200: ext_noise must match images in shape, dtype and device")
+        n = _noise(ext_noise, t)
     out = torch.empty_like(t)
     B, H, W, _ = t.shape
     lib = nv.load_library()
@@ -157,9 +164,7 @@ def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=
     lib = nv.load_library()
     with torch.cuda.device(t.device):
         if ext_noise is not None:
-            n = nv.require_cuda(ext_noise, "ext_noise")
-            if n.shape != t.shape or n.dtype != t.dtype or n.device != t.device:
-                raise ValueError("vrgdg_b200: ext_noise must match images in shape, dtype and device")
+            n = _noise(ext_noise, t)
             nv.check(lib.vrgdg_chain_apply_ext(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(n),
                                                nv.CHAIN_FAST_MATH if fast_math else 0, nv.stream_ptr(t.device)))
         else:

@@ -42,7 +42,12 @@ enum {
   VRGDG_E_ALIGN = -4         /* pointer not aligned to the element size    -> ValueError   */
 };
 
-enum { VRGDG_F32 = 0, VRGDG_F16 = 1, VRGDG_BF16 = 2 };
+/* VRGDG_U8BGR: frames are uint8 in cv2's BGR order, the reference's video wire format (_frames_to_tensor / _tensor_to_frames,
+ * VRGDG_LUTVideoTools.py:736-752): kernels read x/255.0, swap to RGB, compute in fp32 and write clip(y*255,0,255) truncated, BGR.
+ * Accepted by vrgdg_grain, vrgdg_stencil3x3, vrgdg_lut3d_apply (3 channels), vrgdg_lab_moments, vrgdg_colormatch_apply and the
+ * chain entry points: 6 bytes of HBM traffic per pixel instead of 24, no separate conversion passes.  ext_noise for uint8
+ * frames is float32 [B,H,W,3] in RGB order. */
+enum { VRGDG_F32 = 0, VRGDG_F16 = 1, VRGDG_BF16 = 2, VRGDG_U8BGR = 3 };
 
 /* 3x3 stencil epilogues.  nodes.py:182-209 (box unsharp), :266-289 (laplacian, numpy path),
  * :249-258 (laplacian, torch path: opposite sign), :357-384 (sobel, numpy), :329-349 (sobel, torch: +1e-6) */

@@ -176,6 +176,19 @@ def main():
     back = np.stack(ns["_tensor_to_frames"](back_in), axis=0)
     save("u8", bgr=u8, rgb_float=as_t, float_in=back_in, bgr_out=back)
 
+    # ---- uint8 wire format through the whole chain: decode -> grain -> LUT -> unsharp -> encode (bytes in, bytes out) ----
+    xu = (natural_frames(2, 72, 96, seed=71) * 255.0).round().clamp(0, 255).to(torch.uint8).numpy()[..., ::-1].copy()   # BGR bytes
+    ft = ns["_frames_to_tensor"](list(xu))
+    torch.manual_seed(9)
+    zu = torch.randn_like(ft)
+    torch.manual_seed(9)
+    ga = nodes["FastFilmGrain"]().apply_grain(ft, 0.04, 0.5, 0)[0]
+    gb = node.apply_lut(ga, v33, "cpu", 10.0)[0]
+    gc = nodes["FastUnsharpSharpen"]().apply_unsharp(gb, 0.5, False)[0]
+    save("u8chain", bgr_in=xu, z=zu, grain_only=np.stack(ns["_tensor_to_frames"](ga)), lut_only=np.stack(ns["_tensor_to_frames"](node.apply_lut(ft, v33, "cpu", 10.0)[0])),
+         unsharp_only=np.stack(ns["_tensor_to_frames"](nodes["FastUnsharpSharpen"]().apply_unsharp(ft, 0.5, False)[0])),
+         grain_lut_unsharp=np.stack(ns["_tensor_to_frames"](gc)))
+
     # ---- node API surface ---------------------------------------------------------------------------------------------
     api = {}
     classes = dict(nodes)

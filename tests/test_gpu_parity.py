@@ -476,3 +476,59 @@ def test_full_chain_with_colormatch_partition_invariance(pkg, cuda_device):
     c = pkg.ops.lut3d_apply(b, lut["lut"], [0, 0, 0], [1, 1, 1], 1.0, 0.0)
     d = pkg.ops.stencil3x3(c, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
     assert maxdiff(whole, d) <= 5e-6
+
+
+# ------------------------------------------------------------------------------------------------------
+# uint8 BGR wire format fused into the kernels: bytes in, bytes out, 6 B/px of traffic
+# ------------------------------------------------------------------------------------------------------
+def test_u8_frames_through_every_stage_bit_exact(pkg, cuda_device):
+    """reference: _frames_to_tensor -> node(s) -> _tensor_to_frames on cv2 BGR bytes; ours: one kernel on the bytes.
+    Truncating clip(x*255) makes bytes sensitive to the last bit, so this only holds because every stage reproduces the
+    reference's roundings."""
+    nv = pkg._native
+    g = load_golden("u8chain")
+    x = t(g["bgr_in"]).to(cuda_device)
+    z = t(g["z"]).to(cuda_device)
+    lut = _lut33(pkg)
+    assert x.dtype == torch.uint8
+    out = pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=0, ext_noise=z)
+    assert out.dtype == torch.uint8 and torch.equal(out.cpu(), t(g["grain_only"]))
+    assert torch.equal(pkg.ops.lut3d_apply(x, lut["lut"], [0, 0, 0], [1, 1, 1], 1.0, 0.0).cpu(), t(g["lut_only"]))
+    u = pkg.ops.stencil3x3(x, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
+    assert nv.last_tile_path() == "tma" and torch.equal(u.cpu(), t(g["unsharp_only"]))
+    os.environ["VRGDG_NO_TMA"] = "1"
+    try:
+        assert torch.equal(pkg.ops.stencil3x3(x, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE), u)
+    finally:
+        del os.environ["VRGDG_NO_TMA"]
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), lut=dict(lut_data=lut, strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    fused = chain(x, ext_noise=z)
+    assert fused.dtype == torch.uint8 and torch.equal(fused.cpu(), t(g["grain_lut_unsharp"]))
+    # the production arithmetic (contracted FMAs) may flip a byte only where x*255 sits within ~1e-5 of an integer
+    fast = chain(x, ext_noise=z, fast_math=True).cpu().int()
+    d = (fast - t(g["grain_lut_unsharp"]).int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3
+
+
+def test_u8_chain_equals_float_chain_on_decoded_frames(pkg, cuda_device):
+    """bytes path == explicit codec kernels around the fp32 path (same generator, same arithmetic), at 1080p"""
+    nv = pkg._native
+    x = (natural_frames(3, 1080, 1920, seed=72, device=cuda_device) * 255).round().clamp(0, 255).to(torch.uint8)
+    lut = _lut33(pkg)
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=5), lut=dict(lut_data=lut, strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    a = chain(x, first_frame=4)
+    assert nv.last_tile_path() == "tma"
+    b = pkg.ops.rgb_to_u8bgr(chain(pkg.ops.u8bgr_to_rgb(x), first_frame=4))
+    d = (a.int() - b.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-4      # identical kernels; only FMA contraction order could differ
+    # post-grain on bytes (enhancer chain) and partition invariance
+    eff = pkg.chain.PostChain(stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.8),
+                              post_grain=dict(intensity=0.04, saturation_mix=0.5, seed=42, seed_mode=nv.SEED_PER_FRAME), device=cuda_device)
+    whole = eff(x, first_frame=7)
+    parts = torch.cat([eff(x[:2].contiguous(), first_frame=7), eff(x[2:].contiguous(), first_frame=9)])
+    assert torch.equal(whole, parts)
+    ref = pkg.ops.rgb_to_u8bgr(eff(pkg.ops.u8bgr_to_rgb(x), first_frame=7))
+    d2 = (whole.int() - ref.int()).abs()
+    assert int(d2.max()) <= 1 and float((d2 > 0).float().mean()) < 1e-4
