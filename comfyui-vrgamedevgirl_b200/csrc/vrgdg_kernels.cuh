@@ -303,14 +303,14 @@ template <typename T, int MASK> struct TileCfg {
   static constexpr bool WORK = (sizeof(T) == 1) || ((MASK != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
   static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
-  static constexpr int PADL = sizeof(T) == 1 ? 4 : 16 / (int)sizeof(T);   // box starts PADL elements left of the tile (>= 3, even)
-  static constexpr int TXE = 240;                     // output elements per tile row (multiple of 6 and of VEC)
+  static constexpr int PADL = 16 / (int)sizeof(T);    // box starts 16 BYTES left of the tile: TMA needs a 16-byte aligned start address
+  static constexpr int TXE = sizeof(T) == 1 ? 216 : 240;   // output elements per tile row (multiple of 6 and of VEC; PADL + TXE + 3 <= BX)
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
   static constexpr int THREADS = HEAVY ? 480 : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
   static constexpr int MINB = HEAVY ? 1 : 2;
   static constexpr int COLS = TXE / VEC;              // threads across
-  static constexpr int RG = (HEAVY ? 480 : 240) / COLS;   // row groups (active threads / COLS)
+  static constexpr int RG = (THREADS / COLS) >= 8 ? 8 : 4;   // row groups: COLS*RG active threads
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
@@ -615,7 +615,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
-          const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of 240)
+          const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of TXE, TXE of 6)
       for (int i = tid; i < ROWS * C::PAIRS; i += NT) {
         const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
         const int y = y0 - 1 + r, pair = pair0 + kx;
