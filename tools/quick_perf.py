@@ -68,6 +68,26 @@ def main():
                 sums = ops.lab_moments(x)
                 params = ops.colormatch_params(sums, sums[:1].contiguous())
                 report(f"colormatch_apply/{tag}", timeit(lambda: ops.colormatch_apply(x, params, 1.0, 0.0)), npix, bpp)
+            if dist == "nat" and tag == "4k_f32":
+                # configs[2] / configs[3] shapes at a reduced batch: the colour-match node path (moments + params + apply = 2 passes)
+                # and the full chain grain -> colour match -> LUT -> unsharp (moments pass + fused kernel)
+                ref = natural_frames(1, H, W, seed=9, dtype=dt, device=dev)
+                ref_sums = ops.lab_moments(ref)
+                def cm_node():
+                    p = ops.colormatch_params(ops.lab_moments(x), ref_sums)
+                    return ops.colormatch_apply(x, p, 1.0, 0.0)
+                report(f"config3_colormatch_node/{tag}", timeit(cm_node), npix, bpp)
+                full = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(ref_sums=ref_sums, strength=1.0),
+                                           lut=dict(lut_data=lut, strength=10.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=dev)
+                report(f"config4_full_chain/{tag}", timeit(lambda: full(x, out=out)), npix, bpp)
+                u8 = (x * 255).round().clamp(0, 255).to(torch.uint8)
+                u8o = torch.empty_like(u8)
+                report(f"chain_g_l_u/4k_u8bgr", timeit(lambda: chain(u8, out=u8o)), npix, 6)
+                eff = pkg.chain.PostChain(stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5),
+                                          post_grain=dict(intensity=0.04, saturation_mix=0.5, seed=42, seed_mode=nv.SEED_PER_FRAME), device=dev)
+                report(f"enhancer_unsharp_grain/4k_u8bgr", timeit(lambda: eff(u8, out=u8o)), npix, 6)
+                report(f"enhancer_unsharp_grain/{tag}", timeit(lambda: eff(x, out=out)), npix, bpp)
+                del u8, u8o, ref
             del x, out
             torch.cuda.empty_cache()
 
