@@ -241,9 +241,9 @@ def run_b200(args):
         traffic, prof = recorded_traffic()
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 arithmetic, f16 frames",
+            "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "height": H, "width": W, "lut": os.path.basename(LUT_FILE),
+            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "height": H, "width": W, "frame_dtype": "f16", "lut": os.path.basename(LUT_FILE),
                        "distribution": "natural-like (4 octaves of upsampled noise + 2% white)", "parallelism": "frame-sharded dp%d" % world,
                        "l2": "input (796 MB per GPU) and output are each larger than L2 (126 MB); no flush needed", "tile_path": tile_path},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

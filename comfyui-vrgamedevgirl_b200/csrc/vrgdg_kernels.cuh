@@ -304,7 +304,8 @@ template <typename T, int MASK> struct TileCfg {
   static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
   static constexpr int PADL = 16 / (int)sizeof(T);    // box starts 16 BYTES left of the tile: TMA needs a 16-byte aligned start address
-  static constexpr int TXE = sizeof(T) == 1 ? 216 : 240;   // output elements per tile row (multiple of 6 and of VEC; PADL + TXE + 3 <= BX)
+  static constexpr int TXE = sizeof(T) == 1 ? 192 : 240;   // output elements per tile row: multiple of 6 and of VEC, TXE*sizeof(T) % 16 == 0 (every box start
+                                                            // must be 16-byte aligned: an unaligned start is an illegal instruction), PADL + TXE + 3 <= BX
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
   static constexpr int THREADS = HEAVY ? 480 : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
