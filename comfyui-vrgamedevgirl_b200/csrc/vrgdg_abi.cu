@@ -415,6 +415,7 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
   Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
   Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;
   grain_make_key(Q.pseed, Q.pseed_mode, Q.pkey);
+  if (Q.post_enabled && mask == 0) mask = ST_POST;    // pure stencil + post grain: one Philox call per pixel pair via the grain plane
   return run_tile(in, out, B, H, W, dtype, Q, mask, exact, ctx);
 }
 

@@ -105,6 +105,7 @@ cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, Tile
     return launch_tile_k<T, M, true>(tmap, in, out, Q, ctx);
   switch (mask) {
     VRGDG_TL(0) VRGDG_TL(1) VRGDG_TL(2) VRGDG_TL(3) VRGDG_TL(4) VRGDG_TL(5) VRGDG_TL(6) VRGDG_TL(7)
+    VRGDG_TL(8)     // stencil + post grain staged in a shared-memory plane (the enhancer chain)
     default: return cudaErrorInvalidValue;
   }
 #undef VRGDG_TL

@@ -15,7 +15,7 @@
 
 namespace vrgdg {
 
-enum { ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4 };
+enum { ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4, ST_POST = 8 /* k_tile only: post-grain values staged in a shared-memory plane */ };
 
 // ---- element conversion -------------------------------------------------------------------------
 template <typename T> struct Elem;
@@ -300,7 +300,8 @@ struct TileParams {
 // 4 elements per row (16-byte shared loads at a 16-byte lane stride are bank-conflict free; 32-byte strides are not).
 template <typename T, int MASK> struct TileCfg {
   static constexpr bool HEAVY = (MASK & ST_LUT) != 0;
-  static constexpr bool WORK = (sizeof(T) == 1) || ((MASK != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
+  static constexpr bool WORK = (sizeof(T) == 1) || (((MASK & 7) != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
+  static constexpr bool GPLANE = (MASK & ST_POST) != 0;   // grain of the post stage, one Philox call per pixel pair, kept in its own fp32 plane
   static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
   static constexpr int PADL = 16 / (int)sizeof(T);    // box starts 16 BYTES left of the tile: TMA needs a 16-byte aligned start address
@@ -315,7 +316,7 @@ template <typename T, int MASK> struct TileCfg {
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
-  static constexpr int NS = HEAVY ? 2 : 3;            // pipeline stages
+  static constexpr int NS = (HEAVY || GPLANE) ? 2 : 3;   // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
   static_assert(TY % RG == 0 && COLS * RG <= THREADS, "thread mapping");
@@ -326,6 +327,7 @@ constexpr size_t tile_smem_bytes() {
   using C = TileCfg<T, MASK>;
   size_t s = (size_t)C::NS * C::STAGE_BYTES;
   if (C::WORK) s += (size_t)C::ROWS * C::BX * 4;      // fp32 work tile
+  if (C::GPLANE) s += (size_t)C::ROWS * C::BX * 4;    // post-grain plane
   return s + 64 /* mbarriers */ + 128 /* alignment slack */;
 }
 
@@ -436,8 +438,8 @@ __device__ __forceinline__ void store_elems(T* __restrict__ out, const TileParam
 }
 
 template <typename T, int OP, int MASK, bool XS>
-__device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T* __restrict__ out, const TileParams& Q,
-                                             int frame, int y0, int x0e) {
+__device__ __forceinline__ void stencil_rows(const T* raw, const float* work, const float* gplane, T* __restrict__ out,
+                                             const TileParams& Q, int frame, int y0, int x0e) {
   using C = TileCfg<T, MASK>;
   constexpr bool WORK = C::WORK;
   constexpr int VEC = C::VEC, BX = C::BX, PADL = C::PADL, WN = VEC + 6;
@@ -473,7 +475,15 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
         o[e] = clamp01(fmaf(Q.strength, c1[e] - blur, c1[e]));                 // img + s*(img - blur)
         h0[e] = h1[e]; h1[e] = h2; c1[e] = wr[e + 3];
       }
-      if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
+      if constexpr (C::GPLANE) {
+        const float4* gp = reinterpret_cast<const float4*>(gplane + (rbase + j + 1) * BX + PADL + f0);
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) {
+          const float4 gv = gp[q];
+          o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
+          o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
+        }
+      } else if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
     }
   } else {
@@ -491,7 +501,15 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, T*
                       w[2][e], w[2][e + 3], w[2][e + 6]};
         o[e] = XS ? stencil_epilogue_exact(OP, n, Q.strength) : stencil_epilogue(OP, n, Q.strength);
       }
-      if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
+      if constexpr (C::GPLANE) {
+        const float4* gp = reinterpret_cast<const float4*>(gplane + (rbase + j + 1) * BX + PADL + f0);
+#pragma unroll
+        for (int q = 0; q < VEC / 4; ++q) {
+          const float4 gv = gp[q];
+          o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
+          o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
+        }
+      } else if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
 #pragma unroll
       for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
@@ -542,8 +560,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
   const uint32_t smem_a = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((smem_a + 127u) & ~127u) - smem_a);
   T* stage0 = reinterpret_cast<T*>(base);
+  constexpr bool GPLANE = C::GPLANE;
   float* work = reinterpret_cast<float*>(base + (size_t)NS * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NS * C::STAGE_BYTES + (WORK ? ROWS * BX * 4 : 0));
+  float* gplane = reinterpret_cast<float*>(base + (size_t)NS * C::STAGE_BYTES + (WORK ? ROWS * BX * 4 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)NS * C::STAGE_BYTES + (WORK ? ROWS * BX * 4 : 0) + (GPLANE ? ROWS * BX * 4 : 0));
 
   const int tid = threadIdx.x;
   // total_tiles < 2^31 (checked on the host): 32-bit tile arithmetic, no 64-bit divisions per tile
@@ -608,7 +628,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
 
     // ---- per-pixel pre-stages over the halo tile (grain / colour match / LUT), result in fp32 ----
     // one task = one generator pixel pair (2 horizontally adjacent pixels): one Philox call, two independent LUT gathers in flight
-    if (MASK != 0 || WORK) {
+    if ((MASK & 7) != 0 || WORK || GPLANE) {
       const PointParams& P = Q.P;
       constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
       constexpr bool BGR = Io<T>::BGR;
@@ -628,6 +648,21 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
         const bool in_b = need_b && rowin && pxa + 1 >= 0 && pxa + 1 < Q.W;
         // staged elements so..so+5 (pixel a = so..so+2, pixel b = so+3..so+5) move as three 2-element words: lane stride is
         // 6 elements, so 32/64-bit shared accesses are bank-conflict free.  Word 0 lies left of the box when kx == 0.
+        if (GPLANE) {
+          // post-grain values of this pair (added after the stencil): I*(s*z' + (1-s)*z_g) per element, memory channel order
+          float gz[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (rowin && pair >= 0 && pxa < Q.W) {
+            float z[6];
+            grain_pair_normals(grain_pair_bits(Q.pkey, pgf, (uint32_t)pair, (uint32_t)y), z);
+            const float gy0 = Q.poms * z[1], gy1 = Q.poms * z[4];
+            const float r0 = fmaf(2.0f * Q.ps, z[0], gy0), g0 = fmaf(Q.ps, z[1], gy0), b0 = fmaf(3.0f * Q.ps, z[2], gy0);
+            const float r1 = fmaf(2.0f * Q.ps, z[3], gy1), g1 = fmaf(Q.ps, z[4], gy1), b1 = fmaf(3.0f * Q.ps, z[5], gy1);
+            gz[0] = BGR ? b0 : r0; gz[1] = g0; gz[2] = BGR ? r0 : b0;
+            gz[3] = BGR ? b1 : r1; gz[4] = g1; gz[5] = BGR ? r1 : b1;
+          }
+          pair_store6(gplane + so, kx > 0, gz);
+        }
+        if ((MASK & 7) == 0 && !WORK) continue;               // nothing to do to the pixel values themselves
         float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (in_a | in_b) {
           pair_load6<T>(raw + so, kx > 0, e);
@@ -667,21 +702,21 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const float* wt = WORK ? work : nullptr;
       if (Q.exact_stencil) {   // uniform; one specialised row loop per epilogue and arithmetic variant
         switch (Q.op) {
-          case 1: stencil_rows<T, 1, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 2: stencil_rows<T, 2, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 4: stencil_rows<T, 4, MASK, true>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          default: stencil_rows<T, 0, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 1: stencil_rows<T, 1, MASK, true>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 2: stencil_rows<T, 2, MASK, true>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 4: stencil_rows<T, 4, MASK, true>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          default: stencil_rows<T, 0, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
         }
       } else {
         switch (Q.op) {
-          case 1: stencil_rows<T, 1, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 2: stencil_rows<T, 2, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 4: stencil_rows<T, 4, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
-          default: stencil_rows<T, 0, MASK, false>(raw, wt, out, Q, frame, y0, x0e); break;
+          case 1: stencil_rows<T, 1, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 2: stencil_rows<T, 2, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 3: stencil_rows<T, 3, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 4: stencil_rows<T, 4, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          case 5: stencil_rows<T, 5, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
+          default: stencil_rows<T, 0, MASK, false>(raw, wt, gplane, out, Q, frame, y0, x0e); break;
         }
       }
     }
