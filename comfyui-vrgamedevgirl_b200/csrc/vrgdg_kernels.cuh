@@ -35,7 +35,12 @@ template <> struct Elem<__nv_bfloat16> {
 // uint8 frames are the reference's video wire format (cv2 BGR bytes): x/255.0 on the way in, clip(x*255,0,255) TRUNCATED on
 // the way out (VRGDG_LUTVideoTools.py:736-752), channel order swapped to RGB inside the kernels.
 template <> struct Elem<uint8_t> {
-  static __device__ __forceinline__ float ld(uint8_t v) { return divx((float)v, 255.0f); }
+  // v/255.0f, correctly rounded, without the division sequence: q = v*r, q' = fma(fma(-255,q,v), r, q) equals the IEEE quotient
+  // for every one of the 256 byte values (checked exhaustively, tests/test_host_logic.py::test_u8_division_identity)
+  static __device__ __forceinline__ float ld(uint8_t v) {
+    const float r = 1.0f / 255.0f, f = (float)v, q = __fmul_rn(f, r);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q, f), r, q);
+  }
   static __device__ __forceinline__ uint8_t st(float v) { return (uint8_t)fminf(fmaxf(mulx(v, 255.0f), 0.0f), 255.0f); }
 };
 
@@ -636,7 +641,8 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
-          const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of TXE, TXE of 6)
+      const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
+      const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of TXE, TXE of 6)
       for (int i = tid; i < ROWS * C::PAIRS; i += NT) {
         const int r = i / C::PAIRS, kx = i - r * C::PAIRS;
         const int y = y0 - 1 + r, pair = pair0 + kx;

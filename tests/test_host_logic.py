@@ -148,3 +148,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "vrgdg_oracle" not in text and "ref_harness" not in text and "/root/reference" not in text, f
+
+
+def test_u8_division_identity():
+    """Elem<uint8_t>::ld computes v/255.0f as q' = fma(fma(-255, q, v), r, q), q = v*r, r = fl(1/255): must equal the IEEE quotient
+    (what numpy's astype(float32)/255.0 produces) for all 256 byte values.  Exact rational arithmetic emulates the FMAs."""
+    from fractions import Fraction
+
+    def rn32(fr):
+        c = np.float32(float(fr))
+        cands = [np.nextafter(c, np.float32(-np.inf), dtype=np.float32), c, np.nextafter(c, np.float32(np.inf), dtype=np.float32)]
+        return min(cands, key=lambda v: (abs(Fraction(float(v)) - fr), int(np.float32(v).view(np.uint32)) & 1))
+
+    r = np.float32(1.0) / np.float32(255.0)
+    for v in range(256):
+        q = rn32(Fraction(v) * Fraction(float(r)))
+        res = rn32(Fraction(v) - Fraction(255) * Fraction(float(q)))
+        q2 = rn32(Fraction(float(res)) * Fraction(float(r)) + Fraction(float(q)))
+        assert q2 == np.float32(v) / np.float32(255.0), v
