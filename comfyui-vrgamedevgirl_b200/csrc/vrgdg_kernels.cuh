@@ -314,7 +314,10 @@ template <typename T, int MASK> struct TileCfg {
                                                             // must be 16-byte aligned: an unaligned start is an illegal instruction), PADL + TXE + 3 <= BX
   static constexpr int TY = 32;                       // output rows per tile
   static constexpr int ROWS = TY + 2;
-  static constexpr int THREADS = HEAVY ? 480 : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
+#ifndef VRGDG_HEAVY_THREADS
+#define VRGDG_HEAVY_THREADS 480
+#endif
+  static constexpr int THREADS = HEAVY ? VRGDG_HEAVY_THREADS : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
   static constexpr int MINB = HEAVY ? 1 : 2;
   static constexpr int COLS = TXE / VEC;              // threads across
   static constexpr int RG = (THREADS / COLS) >= 8 ? 8 : 4;   // row groups: COLS*RG active threads

@@ -532,3 +532,31 @@ def test_u8_chain_equals_float_chain_on_decoded_frames(pkg, cuda_device):
     ref = pkg.ops.rgb_to_u8bgr(eff(pkg.ops.u8bgr_to_rgb(x), first_frame=7))
     d2 = (whole.int() - ref.int()).abs()
     assert int(d2.max()) <= 1 and float((d2 > 0).float().mean()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------
+# function-level drop-ins (video_tools.py: the reference's module-level helper names)
+# ------------------------------------------------------------------------------------------------------
+def test_video_tools_helpers_match_reference_outputs(pkg, cuda_device):
+    import importlib
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    g = load_golden("lut")
+    out = vt._apply_lut_tensor(t(g["x"]), "B200 Vintage 33.cube", 7.0, "cpu")          # VRGDG_LUTVideoTools.py:172-185
+    assert out.device.type == "cpu" and torch.equal(out, t(g["tensor_fn_s7"]))
+    e = load_golden("effects")
+    st = {"sharpen_enabled": True, "sharpen_strength": 0.8, "grain_enabled": False, "use_gpu": False}
+    assert torch.equal(vt._apply_effects_batch(t(e["xe"]), st, 7), t(e["sharp_only"]))   # EnhancerNodes.py:278-294, numpy-path unsharp
+    st2 = dict(st, grain_enabled=True, grain_intensity=0.04, saturation_mix=0.5, seed=42)
+    whole = vt._apply_effects_batch(t(e["xe"]), st2, 7)
+    parts = torch.cat([vt._apply_effects_batch(t(e["xe"])[:1], st2, 7), vt._apply_effects_batch(t(e["xe"])[1:], st2, 8)])
+    assert whole.device.type == "cpu" and torch.equal(whole, parts)                      # the reference's own batch-boundary invariant
+    d = (whole - t(e["sharp_only"]))
+    assert 0.02 < float(d[..., 1].std()) < 0.06 and not torch.equal(whole, t(e["sharp_only"]))
+    assert torch.equal(vt._apply_unsharp(t(e["xe"]), 0.8, False), t(e["sharp_only"]))
+    assert vt._apply_unsharp(t(e["xe"]), 0.0, False) is not None and torch.equal(vt._apply_seeded_grain(t(e["xe"]), 0.0, 0.5, 1, 0), t(e["xe"]))
+    u = load_golden("u8")
+    assert torch.equal(vt._frames_to_tensor(list(u["bgr"])).cpu(), t(u["rgb_float"]))     # LUTVideoTools.py:736-743
+    frames = vt._tensor_to_frames(t(u["float_in"]))
+    assert np.array_equal(np.stack(frames), u["bgr_out"])                                 # :746-752, truncation
+    fg = vt._apply_film_grain_tensor(t(e["xe"]), 0.04, 0.5, "cpu", seed=11)
+    assert torch.equal(fg, vt._apply_film_grain_tensor(t(e["xe"]), 0.04, 0.5, "cpu", seed=11)) and not torch.equal(fg, t(e["xe"]))
