@@ -25,6 +25,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if "reference" in sys.argv:      # the CPU arm uses every host thread; torchrun would otherwise pin OMP_NUM_THREADS=1
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 
 PKG = "comfyui-vrgamedevgirl_b200"
