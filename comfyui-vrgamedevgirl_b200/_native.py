@@ -59,6 +59,21 @@ class ChainDesc(ctypes.Structure):
     ]
 
 
+class AdjustDesc(ctypes.Structure):
+    """struct vrgdg_adjust_desc (include/vrgdg_b200.h)."""
+
+    _fields_ = [
+        ("enabled", ctypes.c_int32),
+        ("offset_rgb", ctypes.c_float * 3),
+        ("exposure", ctypes.c_float), ("contrast", ctypes.c_float), ("saturation", ctypes.c_float),
+        ("highlights", ctypes.c_float), ("shadows", ctypes.c_float), ("whites", ctypes.c_float), ("blacks", ctypes.c_float),
+        ("clarity_on", ctypes.c_int32), ("sharpen_on", ctypes.c_int32), ("blur_kernel", ctypes.c_int32),
+        ("clarity", ctypes.c_float), ("sharpen", ctypes.c_float),
+        ("fade_on", ctypes.c_int32), ("vignette_on", ctypes.c_int32),
+        ("fade_mul", ctypes.c_float), ("fade_add", ctypes.c_float), ("vignette", ctypes.c_float),
+    ]
+
+
 _vp, _i, _i64, _u64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -82,6 +97,8 @@ SIGNATURES = {
     "vrgdg_chain_apply": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp]),
     "vrgdg_chain_apply_ext": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _i, _vp]),
     "vrgdg_chain_lab_moments": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp, _i64, _vp]),
+    "vrgdg_adjust_scratch_bytes": (_i64, [_i, _i, _i, ctypes.POINTER(AdjustDesc)]),
+    "vrgdg_adjust": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(AdjustDesc), _vp, _vp, _vp, _i64, _vp]),
     "vrgdg_u8bgr_to_rgb": (_i, [_vp, _vp, _i64, _i, _vp]),
     "vrgdg_rgb_to_u8bgr": (_i, [_vp, _vp, _i64, _i, _vp]),
 }

@@ -2,6 +2,7 @@
 // Validates arguments, builds TMA tensor maps, dispatches on dtype, never throws.
 #include "../../include/vrgdg_b200.h"
 #include "vrgdg_kernels.cuh"
+#include "vrgdg_adjust.cuh"
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
@@ -443,6 +444,47 @@ int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, cons
   }
   return moments_common(in, B, H, W, dtype, 0, H, desc->grain_enabled ? &P : nullptr, sums, scratch, scratch_bytes, stream,
                         "vrgdg_chain_lab_moments");
+}
+
+int64_t vrgdg_adjust_scratch_bytes(int B, int H, int W, const vrgdg_adjust_desc* d) {
+  if (!d || B < 0 || H < 0 || W < 0 || !d->enabled) return 0;
+  const int n = (d->clarity_on ? 1 : 0) + (d->sharpen_on ? 1 : 0);
+  return (int64_t)n * B * H * W * 3 * (int64_t)sizeof(float);
+}
+
+int vrgdg_adjust(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_adjust_desc* d, const float* xx,
+                 const float* yy, void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!d) return fail(VRGDG_E_INVALID, "vrgdg_adjust: null descriptor");
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_adjust");
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (d->enabled && d->vignette_on && (!xx || !yy)) return fail(VRGDG_E_INVALID, "vrgdg_adjust: vignette needs the xx / yy ramps");
+  if (d->enabled && d->clarity_on && (d->blur_kernel < 1 || d->blur_kernel > 9 || d->blur_kernel % 2 == 0 ||
+                                      (d->blur_kernel >= 3 && (d->blur_kernel / 2 >= H || d->blur_kernel / 2 >= W))))
+    return fail(VRGDG_E_INVALID, "vrgdg_adjust: blur kernel %d invalid for %d x %d frames", d->blur_kernel, H, W);
+  const int64_t need = vrgdg_adjust_scratch_bytes(B, H, W, d);
+  if (need > 0 && (!scratch || scratch_bytes < need)) return fail(VRGDG_E_INVALID, "vrgdg_adjust: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)need);
+  if (need > 0 && (reinterpret_cast<uintptr_t>(scratch) & 3u)) return fail(VRGDG_E_ALIGN, "vrgdg_adjust: scratch must be 4-byte aligned");
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  AdjustParams A;
+  memset(&A, 0, sizeof(A));
+  A.B = B; A.H = H; A.W = W;
+  for (int i = 0; i < 3; ++i) A.off[i] = d->offset_rgb[i];
+  A.exposure = d->exposure; A.contrast = d->contrast; A.saturation = d->saturation;
+  A.hl = d->highlights; A.sh = d->shadows; A.wh = d->whites; A.bl = d->blacks;
+  A.clarity_on = d->clarity_on; A.sharpen_on = d->sharpen_on; A.kbox = d->blur_kernel;
+  A.clarity = d->clarity; A.sharpen = d->sharpen;
+  A.fade_on = d->fade_on; A.vignette_on = d->vignette_on;
+  A.fade_mul = d->fade_mul; A.fade_add = d->fade_add; A.vignette = d->vignette;
+  A.xx = xx; A.yy = yy;
+  float* s1 = reinterpret_cast<float*>(scratch);
+  float* s2 = s1 ? s1 + (size_t)B * H * W * 3 : nullptr;
+#define AJ(T) launch_adjust<T>(in, out, A, d->enabled ? 1 : 0, s1, s2, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, AJ);
+#undef AJ
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_adjust");
+  return VRGDG_OK;
 }
 
 int vrgdg_u8bgr_to_rgb(const uint8_t* in, void* out, int64_t npix, int dtype, void* stream) {

@@ -1,0 +1,222 @@
+// vrgdg_adjust.cuh — the Builder UI's "adjust" pass (_apply_adjust_tensor, VRGDG_LUTVideoTools.py:307-391):
+// temperature/tint offset, exposure, contrast, saturation, highlight/shadow/white/black masks   (stage A, per pixel)
+// clarity  = x + (x - box_k(x, reflect pad)) * clarity * 1.55 * (0.35 + midtone * 0.65), k = min(9, odd(H), odd(W))   (stage C)
+// sharpen  = x + (x - box_3(x, replicate pad)) * sharpen * 5                                                          (stage S)
+// fade, vignette, clamp                                                                                               (stage D)
+//
+// Every operation is evaluated in the reference's order with one fp32 rounding per op (scalars are Python doubles rounded to
+// fp32 where torch rounds them), and both box sums run sequentially in avg_pool2d's row-major window order, so the result is
+// bit-identical to the reference's CPU tensor path for fp32 (and, through the exact codecs, uint8) frames.
+//
+// Kernels: k_adjust_point (A [+D]) streaming; k_adjust_box<MODE> (C or S [+D]) shared-memory tiles of an fp32 scratch frame.
+// Bound: k_adjust_point HBM; k_adjust_box FADD issue (k*k sequential adds per element: 81 for clarity).
+#pragma once
+#include "vrgdg_kernels.cuh"
+
+namespace vrgdg {
+
+struct AdjustParams {
+  int B, H, W;
+  // stage A (all already rounded to fp32 the way torch rounds Python scalars)
+  float off[3];
+  float exposure, contrast, saturation;
+  float hl, sh, wh, bl;               // highlights/220, shadows/220, whites/240, blacks/240
+  // stage C / S
+  int clarity_on, sharpen_on, kbox;   // kbox = blur kernel size (odd, <= 9; < 3 means "blur = x")
+  float clarity, sharpen;
+  // stage D
+  int fade_on, vignette_on;
+  float fade_mul, fade_add;           // (1 - fade*0.35), fade*0.18
+  float vignette;
+  const float* xx;                    // torch.linspace(-1, 1, W) [W]
+  const float* yy;                    // torch.linspace(-1, 1, H) [H]
+};
+
+__device__ __forceinline__ float adj_luma(float r, float g, float b) {
+  return addx(addx(mulx(r, 0.2126f), mulx(g, 0.7152f)), mulx(b, 0.0722f));
+}
+
+// stage A on one RGB pixel (input already clamped by the caller)
+__device__ __forceinline__ void adjust_stage_a(const AdjustParams& A, float& r, float& g, float& b) {
+  float v[3] = {r, g, b};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float o = addx(v[c], A.off[c]);                              // out + tensor([...])
+    o = mulx(o, A.exposure);                                     // out * exposure
+    v[c] = addx(mulx(subx(o, 0.5f), A.contrast), 0.5f);          // (out - 0.5) * contrast + 0.5
+  }
+  const float l1 = adj_luma(v[0], v[1], v[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = addx(l1, mulx(subx(v[c], l1), A.saturation));   // gray + (out - gray) * saturation
+  const float l2 = adj_luma(v[0], v[1], v[2]);
+  const float hm = clamp01(divx(subx(l2, 0.55f), 0.45f));
+  const float sm = clamp01(divx(subx(0.45f, l2), 0.45f));
+  const float wm = clamp01(divx(subx(l2, 0.75f), 0.25f));
+  const float bm = clamp01(divx(subx(0.25f, l2), 0.25f));
+  const float t1 = mulx(hm, A.hl), t2 = mulx(sm, A.sh), t3 = mulx(wm, A.wh), t4 = mulx(bm, A.bl);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = addx(addx(addx(addx(v[c], t1), t2), t3), t4);
+  r = v[0]; g = v[1]; b = v[2];
+}
+
+// stage D on one element at pixel (x, y)
+__device__ __forceinline__ float adjust_stage_d(const AdjustParams& A, float v, float vmask) {
+  if (A.fade_on) v = addx(mulx(v, A.fade_mul), A.fade_add);      // out * (1 - fade*0.35) + fade*0.18
+  if (A.vignette_on) v = mulx(v, vmask);
+  return clamp01(v);
+}
+__device__ __forceinline__ float vignette_mask(const AdjustParams& A, int x, int y) {
+  if (!A.vignette_on) return 1.0f;
+  const float xv = __ldg(A.xx + x), yv = __ldg(A.yy + y);
+  const float d = sqrtx(addx(mulx(xv, xv), mulx(yv, yv)));        // sqrt(xx*xx + yy*yy)
+  const float c = clamp01(divx(subx(d, 0.35f), 1.05f));
+  return subx(1.0f, mulx(mulx(c, A.vignette), 0.75f));           // 1 - clamp(...) * vignette * 0.75
+}
+
+// ---- stage A (+ D when nothing follows): one pixel per thread ------------------------------------------------------------
+template <typename T, bool TO_SCRATCH>
+__global__ void __launch_bounds__(256)
+k_adjust_point(const T* __restrict__ in, T* __restrict__ out, float* __restrict__ scratch, AdjustParams A, int enabled) {
+  constexpr bool BGR = Io<T>::BGR;
+  const int64_t hw = (int64_t)A.H * A.W, total = (int64_t)A.B * hw;
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+    const T* s = in + p * 3;
+    float r = clamp01(Elem<T>::ld(s[BGR ? 2 : 0])), g = clamp01(Elem<T>::ld(s[1])), b = clamp01(Elem<T>::ld(s[BGR ? 0 : 2]));   // source.clamp(0, 1)
+    if (enabled) {
+      adjust_stage_a(A, r, g, b);
+      if (!TO_SCRATCH) {
+        const int64_t pif = p % hw;
+        const int y = (int)(pif / A.W), x = (int)(pif - (int64_t)y * A.W);
+        const float m = vignette_mask(A, x, y);
+        r = adjust_stage_d(A, r, m); g = adjust_stage_d(A, g, m); b = adjust_stage_d(A, b, m);
+      }
+    }
+    if (TO_SCRATCH) {
+      float* d = scratch + p * 3;
+      d[0] = r; d[1] = g; d[2] = b;                              // RGB order in the scratch frame
+    } else {
+      T* d = out + p * 3;
+      d[BGR ? 2 : 0] = Elem<T>::st(r); d[1] = Elem<T>::st(g); d[BGR ? 0 : 2] = Elem<T>::st(b);
+    }
+  }
+}
+
+// ---- stage C (MODE 0, reflect pad, k x k) or S (MODE 1, replicate pad, 3 x 3) on an fp32 RGB scratch frame ----------------------
+// tile = 16 rows x 64 pixels in shared memory; each thread sums the K x K window of its element sequentially in avg_pool2d's
+// row-major order (that order, not a separable sum, is what makes the result bit-identical).
+constexpr int ADJ_TY = 16, ADJ_TXP = 64, ADJ_TXE = ADJ_TXP * 3, ADJ_RMAX = 4;
+constexpr int ADJ_SW = ADJ_TXE + 6 * ADJ_RMAX;        // 216 floats per tile row
+constexpr int ADJ_SH = ADJ_TY + 2 * ADJ_RMAX;         // 24 rows
+
+template <typename T, int MODE, bool LAST>
+__global__ void __launch_bounds__(256)
+k_adjust_box(const float* __restrict__ src, float* __restrict__ dst_scratch, T* __restrict__ out, AdjustParams A, int tiles_x, int tiles_y) {
+  constexpr bool BGR = Io<T>::BGR;
+  __shared__ float tile[ADJ_SH * ADJ_SW];
+  const int R = (MODE == 0) ? A.kbox / 2 : 1, K = 2 * R + 1;
+  const int RW = A.W * 3;
+  const int tiles_per_frame = tiles_x * tiles_y;
+  const int total = A.B * tiles_per_frame;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int frame = t / tiles_per_frame, rem = t - frame * tiles_per_frame;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int y0 = ty * ADJ_TY, x0 = tx * ADJ_TXP;
+    const float* fbase = src + (int64_t)frame * A.H * RW;
+    // cooperative load with padding by index mapping (reflect: -i -> i, n-1+i -> n-1-i ; replicate: clamp)
+    const int rows = ADJ_TY + 2 * R, colsp = ADJ_TXP + 2 * R;
+    for (int i = threadIdx.x; i < rows * colsp; i += 256) {
+      const int rr = i / colsp, cp = i - rr * colsp;
+      int y = y0 - R + rr, x = x0 - R + cp;
+      if (MODE == 0) {
+        y = y < 0 ? -y : (y >= A.H ? 2 * (A.H - 1) - y : y);
+        x = x < 0 ? -x : (x >= A.W ? 2 * (A.W - 1) - x : x);
+        y = max(0, min(y, A.H - 1)); x = max(0, min(x, A.W - 1));      // tiles beyond the image edge (masked later)
+      } else {
+        y = max(0, min(y, A.H - 1)); x = max(0, min(x, A.W - 1));
+      }
+      const float* s = fbase + ((int64_t)y * A.W + x) * 3;
+      float* d = tile + rr * ADJ_SW + cp * 3;
+      d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    }
+    __syncthreads();
+    // 16 x 192 outputs over 256 threads: 12 per thread
+    for (int i = threadIdx.x; i < ADJ_TY * ADJ_TXE; i += 256) {
+      const int ry = i / ADJ_TXE, e = i - ry * ADJ_TXE;
+      const int y = y0 + ry, x = x0 + e / 3, ch = e - (e / 3) * 3;
+      if (y >= A.H || x >= A.W) continue;
+      const float* c0 = tile + (ry + R) * ADJ_SW + e + 3 * R;      // centre element
+      const float xc = *c0;
+      float res = xc;
+      if (K >= 3) {
+        // avg_pool2d: sum over the window in row-major order, then / (K*K)
+        float acc = 0.0f;
+        bool first = true;
+        for (int dy = -R; dy <= R; ++dy) {
+          const float* rowp = c0 + dy * ADJ_SW;
+          for (int dx = -R; dx <= R; ++dx) {
+            const float v = rowp[3 * dx];
+            acc = first ? v : addx(acc, v);
+            first = false;
+          }
+        }
+        const float blur = divx(acc, (float)(K * K));
+        const float detail = subx(xc, blur);
+        if (MODE == 0) {
+          const float* px = c0 - ch;                               // this pixel's r, g, b
+          const float ln = adj_luma(px[0], px[1], px[2]);
+          const float mid = subx(1.0f, clamp01(divx(fabsf(subx(ln, 0.5f)), 0.5f)));
+          const float wgt = addx(0.35f, mulx(mid, 0.65f));
+          res = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
+        } else {
+          res = addx(xc, mulx(mulx(detail, A.sharpen), 5.0f));               // nchw + fine_detail * sharpen * 5.0
+        }
+      }   // K < 3 (frames narrower than 3 pixels): the reference's blur returns x itself, detail == 0, result == x
+      const int64_t o = (((int64_t)frame * A.H + y) * A.W + x) * 3;
+      if (LAST) {
+        const float m = vignette_mask(A, x, y);
+        out[o + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res, m));
+      } else {
+        dst_scratch[o + ch] = res;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+cudaError_t launch_adjust(const void* in, void* out, const AdjustParams& A, int enabled, float* s1, float* s2, const LaunchCtx& ctx) {
+  const int64_t total = (int64_t)A.B * A.H * A.W;
+  if (total == 0) return cudaSuccess;
+  const int pgrid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx.sms * 16);
+  const bool C = enabled && A.clarity_on, S = enabled && A.sharpen_on;
+  const T* tin = reinterpret_cast<const T*>(in);
+  T* tout = reinterpret_cast<T*>(out);
+  if (!C && !S) {
+    k_adjust_point<T, false><<<pgrid, 256, 0, ctx.stream>>>(tin, tout, nullptr, A, enabled);
+    count_launch();
+    return cudaGetLastError();
+  }
+  k_adjust_point<T, true><<<pgrid, 256, 0, ctx.stream>>>(tin, tout, s1, A, enabled);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int tiles_x = (A.W + ADJ_TXP - 1) / ADJ_TXP, tiles_y = (A.H + ADJ_TY - 1) / ADJ_TY;
+  const int64_t tiles = (int64_t)A.B * tiles_x * tiles_y;
+  const int tgrid = (int)std::min<int64_t>(tiles, (int64_t)ctx.sms * 8);
+  const float* cur = s1;
+  if (C) {
+    if (S) k_adjust_box<T, 0, false><<<tgrid, 256, 0, ctx.stream>>>(cur, s2, tout, A, tiles_x, tiles_y);
+    else k_adjust_box<T, 0, true><<<tgrid, 256, 0, ctx.stream>>>(cur, nullptr, tout, A, tiles_x, tiles_y);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    cur = s2;
+  }
+  if (S) {
+    k_adjust_box<T, 1, true><<<tgrid, 256, 0, ctx.stream>>>(cur, nullptr, tout, A, tiles_x, tiles_y);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace vrgdg

@@ -2,6 +2,7 @@
 #pragma once
 #include "vrgdg_kernels.cuh"
 #include <algorithm>
+#include "vrgdg_adjust.cuh"
 #include <string.h>
 
 namespace vrgdg {
@@ -150,6 +151,7 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_lut_rgba<T>(const void*, void*, int64_t, const LutParams&, const LaunchCtx&);               \
   template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
   template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&); \
+  template cudaError_t launch_adjust<T>(const void*, void*, const AdjustParams&, int, float*, float*, const LaunchCtx&);              \
   template void tile_geometry<T>(int, int, int&, int&, int&, int&);
 
 #define VRGDG_INSTANTIATE_CODECS(T)                                                                                       \

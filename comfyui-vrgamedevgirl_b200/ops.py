@@ -186,6 +186,24 @@ def chain_lab_moments(images, desc):
     return sums
 
 
+def adjust(images, desc):
+    """_apply_adjust_tensor with a prepared AdjustDesc (video_tools._adjust_desc builds it from a settings dict)."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    out = torch.empty_like(t)
+    lib = nv.load_library()
+    xx = yy = None
+    if desc.enabled and desc.vignette_on:
+        xx = torch.linspace(-1.0, 1.0, W, dtype=torch.float32).to(t.device)     # the reference's own ramps (:384-385)
+        yy = torch.linspace(-1.0, 1.0, H, dtype=torch.float32).to(t.device)
+    nbytes = int(lib.vrgdg_adjust_scratch_bytes(B, H, W, ctypes.byref(desc)))
+    scratch = torch.empty((nbytes // 4,), dtype=torch.float32, device=t.device) if nbytes else None
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_adjust(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(xx), nv.ptr(yy),
+                                  nv.ptr(scratch), ctypes.c_int64(nbytes), nv.stream_ptr(t.device)))
+    return out
+
+
 def u8bgr_to_rgb(frames_u8, dtype=torch.float32):
     """uint8 BGR [..., 3] CUDA -> RGB float (x/255)."""
     if frames_u8.device.type != "cuda" or frames_u8.dtype != torch.uint8 or frames_u8.shape[-1] != 3:

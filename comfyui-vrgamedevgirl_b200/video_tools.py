@@ -4,6 +4,8 @@ Reference: VRGDG_LUTVideoTools.py (_apply_lut_tensor :172-185, _apply_film_grain
 and VRGDG_StandaloneVideoEnhancerNodes.py (_auto_batch_size :200-210, _apply_unsharp :233-258, _apply_seeded_grain :261-275,
 _apply_effects_batch :278-294).  The decode/encode, ffmpeg and HTTP route glue around them is out of scope.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -35,6 +37,60 @@ def _apply_film_grain_tensor(image_tensor, grain_intensity=0.04, saturation_mix=
     if seed in (None, ""):
         seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
     out = ops.grain(src, intensity, saturation, 1.0 - saturation, int(seed), frame0=0, seed_mode=nv.SEED_PER_CLIP)
+    return out if str(device) != "cpu" else out.to(image_tensor.device)
+
+
+_ADJUST_FIELDS = {"temperature": (-100.0, 100.0), "tint": (-100.0, 100.0), "saturation": (-100.0, 100.0), "exposure": (-100.0, 100.0),
+                  "contrast": (-100.0, 100.0), "highlights": (-100.0, 100.0), "shadows": (-100.0, 100.0), "whites": (-100.0, 100.0),
+                  "blacks": (-100.0, 100.0), "sharpen": (0.0, 100.0), "clarity": (-100.0, 100.0), "vignette": (0.0, 100.0), "fade": (0.0, 100.0)}
+
+
+def _normalize_adjust_settings(settings=None):
+    """VRGDG_LUTVideoTools.py:280-304 (host logic): clamp every slider into its range, non-numeric -> 0."""
+    settings = settings if isinstance(settings, dict) else {}
+    out = {"enabled": settings.get("enabled", True) is not False}
+    for key, (lo, hi) in _ADJUST_FIELDS.items():
+        try:
+            value = float(settings.get(key, 0.0))
+        except Exception:
+            value = 0.0
+        out[key] = max(lo, min(hi, value))
+    return out
+
+
+def _adjust_desc(settings, height, width):
+    """The scalars of _apply_adjust_tensor (:307-391), evaluated in double exactly as the reference's Python expressions do;
+    ctypes rounds them to fp32 where torch rounds a Python scalar that meets an fp32 tensor."""
+    a = _normalize_adjust_settings(settings)
+    d = nv.AdjustDesc()
+    d.enabled = 1 if a["enabled"] else 0
+    d.offset_rgb = (ctypes.c_float * 3)(a["temperature"] / 400.0 - a["tint"] / 900.0, a["tint"] / 450.0, -a["temperature"] / 400.0 - a["tint"] / 900.0)
+    d.exposure = 2.0 ** (a["exposure"] / 100.0)
+    d.contrast = 1.0 + (a["contrast"] / 100.0)
+    d.saturation = 1.0 + (a["saturation"] / 100.0)
+    d.highlights, d.shadows = a["highlights"] / 220.0, a["shadows"] / 220.0
+    d.whites, d.blacks = a["whites"] / 240.0, a["blacks"] / 240.0
+    clarity, sharpen = a["clarity"] / 100.0, a["sharpen"] / 100.0
+    d.clarity, d.sharpen = clarity, sharpen
+    d.clarity_on = 1 if abs(clarity) > 0.001 else 0
+    d.sharpen_on = 1 if sharpen > 0.001 else 0
+    d.blur_kernel = min(9, height if height % 2 else height - 1, width if width % 2 else width - 1)
+    if d.blur_kernel < 3:
+        d.blur_kernel = 1                 # the reference's blur returns its input
+    fade = a["fade"] / 100.0
+    d.fade_on = 1 if fade > 0.0 else 0
+    d.fade_mul, d.fade_add = 1.0 - fade * 0.35, fade * 0.18
+    vignette = a["vignette"] / 100.0
+    d.vignette_on = 1 if vignette > 0.0 else 0
+    d.vignette = vignette
+    return d
+
+
+def _apply_adjust_tensor(image_tensor, settings=None, device="cpu"):
+    """VRGDG_LUTVideoTools.py:307-391 on the GPU (bit-identical for fp32 frames); result on `device` like the reference, or on the
+    input's device when that is "cpu"."""
+    src, dev = _to_cuda(image_tensor, device)
+    out = ops.adjust(src, _adjust_desc(settings, int(src.shape[1]), int(src.shape[2])))
     return out if str(device) != "cpu" else out.to(image_tensor.device)
 
 

@@ -189,6 +189,28 @@ VRGDG_API int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int d
                             const vrgdg_chain_desc* desc, double* sums,
                             void* scratch, int64_t scratch_bytes, void* stream);
 
+/* ---- "adjust" pass of the Builder UI ---------------------------------------------------------------------------
+ * Replaces _apply_adjust_tensor (VRGDG_LUTVideoTools.py:307-391): clamp, temperature/tint offset, exposure, contrast,
+ * saturation, highlight/shadow/white/black masks, clarity (k x k reflect-padded box, k = min(9, odd(H), odd(W))), sharpen
+ * (3 x 3 replicate-padded box), fade, vignette, clamp.  The descriptor carries the scalars exactly as the reference's Python
+ * expressions produce them (the host mirror in video_tools.py evaluates those expressions in double and rounds to fp32 where
+ * torch does); xx / yy are torch.linspace(-1, 1, W / H) on the device (only read when vignette_on).  Bit-identical to the
+ * reference for fp32 frames.  scratch: vrgdg_adjust_scratch_bytes() bytes of device memory (0 when neither clarity nor
+ * sharpen is on). */
+typedef struct vrgdg_adjust_desc {
+  int32_t enabled;
+  float offset_rgb[3];                 /* temperature/400 - tint/900, tint/450, -temperature/400 - tint/900 */
+  float exposure, contrast, saturation;/* 2**(e/100), 1 + c/100, 1 + s/100 */
+  float highlights, shadows, whites, blacks;   /* h/220, s/220, w/240, b/240 */
+  int32_t clarity_on, sharpen_on, blur_kernel;
+  float clarity, sharpen;              /* c/100, s/100 */
+  int32_t fade_on, vignette_on;
+  float fade_mul, fade_add, vignette;  /* 1 - fade*0.35, fade*0.18, v/100 */
+} vrgdg_adjust_desc;
+VRGDG_API int64_t vrgdg_adjust_scratch_bytes(int B, int H, int W, const vrgdg_adjust_desc* desc);
+VRGDG_API int vrgdg_adjust(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_adjust_desc* desc,
+                 const float* xx, const float* yy, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- uint8 BGR wire format -------------------------------------------------------------------------
  * _frames_to_tensor / _tensor_to_frames (VRGDG_LUTVideoTools.py:736-752,
  * VRGDG_StandaloneVideoEnhancerNodes.py:311-324): u8 BGR -> RGB float /255.0 and

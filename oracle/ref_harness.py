@@ -75,5 +75,5 @@ def load_enhancer_helpers():
 def load_lut_video_helpers(iv=None):
     iv = iv if iv is not None else load_iv_adjustments()
     ns = {"torch": torch, "VRGDG_LUTS": iv.VRGDG_LUTS}
-    names = {"_apply_lut_tensor", "_apply_film_grain_tensor"}
+    names = {"_apply_lut_tensor", "_apply_film_grain_tensor", "_normalize_adjust_settings", "_apply_adjust_tensor"}
     return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_LUTVideoTools.py"), names, ns)

@@ -339,6 +339,75 @@ def palette_lut(colors_rgb, lut_size):
 
 
 # --------------------------------------------------------------------------------------------------
+# "adjust" (temperature / tint / exposure / contrast / saturation / tonal masks / clarity / sharpen / fade / vignette)
+# --------------------------------------------------------------------------------------------------
+ADJUST_FIELDS = {"temperature": (-100.0, 100.0), "tint": (-100.0, 100.0), "saturation": (-100.0, 100.0), "exposure": (-100.0, 100.0),
+                 "contrast": (-100.0, 100.0), "highlights": (-100.0, 100.0), "shadows": (-100.0, 100.0), "whites": (-100.0, 100.0),
+                 "blacks": (-100.0, 100.0), "sharpen": (0.0, 100.0), "clarity": (-100.0, 100.0), "vignette": (0.0, 100.0), "fade": (0.0, 100.0)}
+
+
+def normalize_adjust_settings(settings=None):
+    """_normalize_adjust_settings, VRGDG_LUTVideoTools.py:280-304."""
+    settings = settings if isinstance(settings, dict) else {}
+    out = {"enabled": settings.get("enabled", True) is not False}
+    for key, (lo, hi) in ADJUST_FIELDS.items():
+        try:
+            v = float(settings.get(key, 0.0))
+        except Exception:
+            v = 0.0
+        out[key] = max(lo, min(hi, v))
+    return out
+
+
+def _luma(t):
+    return (t[..., 0:1] * 0.2126) + (t[..., 1:2] * 0.7152) + (t[..., 2:3] * 0.0722)
+
+
+def adjust(image_tensor, settings=None):
+    """_apply_adjust_tensor on CPU, VRGDG_LUTVideoTools.py:307-391."""
+    a = normalize_adjust_settings(settings)
+    src = image_tensor.clamp(0.0, 1.0)
+    if not a["enabled"]:
+        return src
+    out = src + torch.tensor([a["temperature"] / 400.0 - a["tint"] / 900.0, a["tint"] / 450.0, -a["temperature"] / 400.0 - a["tint"] / 900.0],
+                             dtype=src.dtype).view(1, 1, 1, 3)
+    out = out * (2.0 ** (a["exposure"] / 100.0))
+    out = (out - 0.5) * (1.0 + (a["contrast"] / 100.0)) + 0.5
+    gray = _luma(out).repeat(1, 1, 1, 3)
+    out = gray + (out - gray) * (1.0 + (a["saturation"] / 100.0))
+    luma = _luma(out)
+    out = out + torch.clamp((luma - 0.55) / 0.45, 0.0, 1.0) * (a["highlights"] / 220.0)
+    out = out + torch.clamp((0.45 - luma) / 0.45, 0.0, 1.0) * (a["shadows"] / 220.0)
+    out = out + torch.clamp((luma - 0.75) / 0.25, 0.0, 1.0) * (a["whites"] / 240.0)
+    out = out + torch.clamp((0.25 - luma) / 0.25, 0.0, 1.0) * (a["blacks"] / 240.0)
+    clarity, sharpen = a["clarity"] / 100.0, a["sharpen"] / 100.0
+    if abs(clarity) > 0.001 or sharpen > 0.001:
+        x = out.permute(0, 3, 1, 2)
+        h, w = int(x.shape[2]), int(x.shape[3])
+        if abs(clarity) > 0.001:
+            k = min(9, h if h % 2 else h - 1, w if w % 2 else w - 1)
+            blur = x if k < 3 else F.avg_pool2d(F.pad(x, (k // 2,) * 4, mode="reflect"), kernel_size=k, stride=1)
+            ln = x[:, 0:1] * 0.2126 + x[:, 1:2] * 0.7152 + x[:, 2:3] * 0.0722
+            mid = 1.0 - torch.clamp(torch.abs(ln - 0.5) / 0.5, 0.0, 1.0)
+            x = x + (x - blur) * clarity * 1.55 * (0.35 + mid * 0.65)
+        if sharpen > 0.001:
+            fine = F.avg_pool2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), kernel_size=3, stride=1)
+            x = x + (x - fine) * sharpen * 5.0
+        out = x.permute(0, 2, 3, 1)
+    fade = a["fade"] / 100.0
+    if fade > 0.0:
+        out = out * (1.0 - fade * 0.35) + fade * 0.18
+    vig = a["vignette"] / 100.0
+    if vig > 0.0:
+        h, w = out.shape[1], out.shape[2]
+        yy = torch.linspace(-1.0, 1.0, h, dtype=out.dtype).view(1, h, 1, 1)
+        xx = torch.linspace(-1.0, 1.0, w, dtype=out.dtype).view(1, 1, w, 1)
+        dist = torch.sqrt((xx * xx) + (yy * yy))
+        out = out * (1.0 - torch.clamp((dist - 0.35) / 1.05, 0.0, 1.0) * vig * 0.75)
+    return out.clamp(0.0, 1.0)
+
+
+# --------------------------------------------------------------------------------------------------
 # uint8 BGR wire format
 # --------------------------------------------------------------------------------------------------
 def frames_to_tensor(frames_bgr_u8):

@@ -189,6 +189,24 @@ def main():
          unsharp_only=np.stack(ns["_tensor_to_frames"](nodes["FastUnsharpSharpen"]().apply_unsharp(ft, 0.5, False)[0])),
          grain_lut_unsharp=np.stack(ns["_tensor_to_frames"](gc)))
 
+    # ---- adjust (_apply_adjust_tensor) --------------------------------------------------------------------------------
+    xa = natural_frames(2, 72, 96, seed=81) * 1.1 - 0.05                      # some values outside [0,1]: the function clamps first
+    adj = {"x": xa}
+    ADJ_CASES = {
+        "pointwise": {"temperature": 30, "tint": -20, "exposure": 25, "contrast": 40, "saturation": -35, "highlights": 50, "shadows": -40, "whites": 20, "blacks": -60},
+        "fade_vignette": {"fade": 40, "vignette": 70, "exposure": -10},
+        "sharpen": {"sharpen": 60, "contrast": 10},
+        "clarity": {"clarity": 80, "saturation": 20},
+        "everything": {"temperature": -45, "tint": 15, "exposure": 12, "contrast": -20, "saturation": 30, "highlights": -30, "shadows": 35, "whites": -15,
+                       "blacks": 25, "sharpen": 35, "clarity": -60, "vignette": 50, "fade": 20},
+        "disabled": {"enabled": False, "exposure": 50},
+    }
+    for name, st in ADJ_CASES.items():
+        adj[name] = lvt["_apply_adjust_tensor"](xa, st, "cpu")
+    adj["tiny_5x7"] = lvt["_apply_adjust_tensor"](xa[:, :5, :7].contiguous(), ADJ_CASES["everything"], "cpu")    # blur kernel shrinks to 5
+    save("adjust", **adj)
+    meta["adjust_cases"] = ADJ_CASES
+
     # ---- node API surface ---------------------------------------------------------------------------------------------
     api = {}
     classes = dict(nodes)

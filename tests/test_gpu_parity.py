@@ -560,3 +560,41 @@ def test_video_tools_helpers_match_reference_outputs(pkg, cuda_device):
     assert np.array_equal(np.stack(frames), u["bgr_out"])                                 # :746-752, truncation
     fg = vt._apply_film_grain_tensor(t(e["xe"]), 0.04, 0.5, "cpu", seed=11)
     assert torch.equal(fg, vt._apply_film_grain_tensor(t(e["xe"]), 0.04, 0.5, "cpu", seed=11)) and not torch.equal(fg, t(e["xe"]))
+
+
+# ------------------------------------------------------------------------------------------------------
+# "adjust" pass: _apply_adjust_tensor, VRGDG_LUTVideoTools.py:307-391
+# ------------------------------------------------------------------------------------------------------
+def test_adjust_tensor_bit_exact_all_cases(pkg, cuda_device, meta):
+    import importlib
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    g = load_golden("adjust")
+    x = t(g["x"])
+    for name, st in meta["adjust_cases"].items():
+        before = pkg._native.launch_count()
+        out = vt._apply_adjust_tensor(x, st, "cpu")
+        assert pkg._native.launch_count() > before
+        assert out.device.type == "cpu" and torch.equal(out, t(g[name])), name
+    # frames narrower than the 9x9 window: the blur kernel shrinks (5x7 -> 5)
+    tiny = vt._apply_adjust_tensor(x[:, :5, :7].contiguous(), meta["adjust_cases"]["everything"], "cpu")
+    assert torch.equal(tiny, t(g["tiny_5x7"]))
+    # device-resident call keeps the result on the GPU; non-numeric / out-of-range sliders are normalised like the reference
+    dev_out = vt._apply_adjust_tensor(x.to(cuda_device), {"exposure": "abc", "contrast": 1e9, "sharpen": -5}, cuda_device)
+    ref = vt._apply_adjust_tensor(x, {"contrast": 100.0}, "cpu")
+    assert dev_out.device.type == "cuda" and torch.equal(dev_out.cpu(), ref)
+
+
+def test_adjust_full_size_properties(pkg, cuda_device, oracle):
+    """1080p: neutral settings == clamp; and the oracle agrees on a whole frame with every stage on (1 frame: ~1 s of CPU)."""
+    import importlib
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    x = natural_frames(1, 1080, 1920, seed=91) * 1.2 - 0.1
+    assert torch.equal(vt._apply_adjust_tensor(x, {}, "cpu"), x.clamp(0, 1))
+    st = {"temperature": 20, "exposure": 10, "contrast": 15, "saturation": 10, "highlights": -20, "shadows": 20, "sharpen": 40, "clarity": 50,
+          "vignette": 30, "fade": 10}
+    assert torch.equal(vt._apply_adjust_tensor(x, st, "cpu"), oracle.adjust(x, st))
+    # uint8 frames: decode -> adjust -> encode in the kernels == codecs around the float path
+    u8 = (x.clamp(0, 1) * 255).round().to(torch.uint8).to(cuda_device)
+    a = pkg.ops.adjust(u8, vt._adjust_desc(st, 1080, 1920))
+    b = pkg.ops.rgb_to_u8bgr(pkg.ops.adjust(pkg.ops.u8bgr_to_rgb(u8), vt._adjust_desc(st, 1080, 1920)))
+    assert a.dtype == torch.uint8 and torch.equal(a, b)

@@ -166,3 +166,17 @@ def test_u8_division_identity():
         res = rn32(Fraction(v) - Fraction(255) * Fraction(float(q)))
         q2 = rn32(Fraction(float(res)) * Fraction(float(r)) + Fraction(float(q)))
         assert q2 == np.float32(v) / np.float32(255.0), v
+
+
+def test_adjust_settings_normalisation_and_descriptor(pkg, oracle):
+    vt = __import__("importlib").import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    for st in ({}, {"enabled": False}, {"sharpen": -3, "fade": 1e9, "tint": "x"}, {"clarity": 0.05}, None, "junk"):
+        assert vt._normalize_adjust_settings(st) == oracle.normalize_adjust_settings(st)
+    d = vt._adjust_desc({"temperature": 40, "tint": -9, "exposure": 50, "clarity": 0.05, "sharpen": 0.2, "fade": 10, "vignette": 0}, 1080, 1920)
+    assert d.enabled == 1 and d.clarity_on == 0 and d.sharpen_on == 1 and d.blur_kernel == 9 and d.fade_on == 1 and d.vignette_on == 0
+    assert d.exposure == np.float32(2.0 ** 0.5) and d.offset_rgb[0] == np.float32(40 / 400.0 - (-9) / 900.0) and d.fade_mul == np.float32(1.0 - 0.1 * 0.35)
+    assert vt._adjust_desc({}, 5, 8).blur_kernel == 5 and vt._adjust_desc({}, 2, 2).blur_kernel == 1 and vt._adjust_desc({}, 4, 100).blur_kernel == 3
+    lib = pkg._native.load_library()
+    import ctypes
+    assert lib.vrgdg_adjust_scratch_bytes(2, 10, 20, ctypes.byref(d)) == 2 * 10 * 20 * 3 * 4
+    assert lib.vrgdg_adjust_scratch_bytes(2, 10, 20, ctypes.byref(vt._adjust_desc({}, 10, 20))) == 0

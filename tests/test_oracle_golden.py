@@ -96,6 +96,18 @@ def test_colormatch_and_chain_restatement(oracle):
     assert torch.equal(oracle.chain_full(t(c["x"]), t(c["z"]), 0.04, 0.5, t(c["ref"]), 1.0, v33, 10.0, 0.5), t(c["grain_cm_lut_unsharp"]))
 
 
+def test_adjust_restatement_bit_exact(oracle):
+    g = load_golden("adjust")
+    with open(os.path.join(GOLDEN, "reference_meta.json"), encoding="utf-8") as fh:
+        cases = json.load(fh)["adjust_cases"]
+    assert set(cases) >= {"pointwise", "fade_vignette", "sharpen", "clarity", "everything", "disabled"}
+    for name, st in cases.items():
+        assert torch.equal(oracle.adjust(t(g["x"]), st), t(g[name])), name
+    assert torch.equal(oracle.adjust(t(g["x"])[:, :5, :7].contiguous(), cases["everything"]), t(g["tiny_5x7"]))
+    assert oracle.normalize_adjust_settings({"sharpen": -3, "fade": 1e9, "tint": "x", "enabled": False}) == dict(
+        oracle.normalize_adjust_settings({}), enabled=False, fade=100.0)
+
+
 def test_u8_restatement(oracle):
     g = load_golden("u8")
     assert torch.equal(oracle.frames_to_tensor(g["bgr"]), t(g["rgb_float"]))
@@ -155,6 +167,9 @@ def test_live_reference_filters_match_oracle(oracle):
     assert torch.equal(enh["_apply_effects_batch"](x, st, 3), oracle.effects_batch(x, st, 3))
     lvt = rh.load_lut_video_helpers()
     assert torch.equal(lvt["_apply_film_grain_tensor"](x, 0.07, 0.4, "cpu", 11), oracle.film_grain_tensor(x, 0.07, 0.4, 11))
+    st = {"temperature": 12, "tint": 7, "exposure": -8, "contrast": 22, "saturation": -11, "shadows": 14, "blacks": -9, "sharpen": 25, "clarity": 33, "fade": 5, "vignette": 44}
+    assert torch.equal(lvt["_apply_adjust_tensor"](x * 1.1 - 0.05, st, "cpu"), oracle.adjust(x * 1.1 - 0.05, st))
+    assert lvt["_normalize_adjust_settings"]({"fade": 500, "clarity": "no"}) == oracle.normalize_adjust_settings({"fade": 500, "clarity": "no"})
 
 
 def test_live_reference_parses_all_its_own_luts_like_the_oracle(oracle, pkg):
