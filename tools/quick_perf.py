@@ -87,6 +87,13 @@ def main():
                                           post_grain=dict(intensity=0.04, saturation_mix=0.5, seed=42, seed_mode=nv.SEED_PER_FRAME), device=dev)
                 report(f"enhancer_unsharp_grain/4k_u8bgr", timeit(lambda: eff(u8, out=u8o)), npix, 6)
                 report(f"enhancer_unsharp_grain/{tag}", timeit(lambda: eff(x, out=out)), npix, bpp)
+                vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+                for name, st in (("adjust_pointwise", {"temperature": 20, "exposure": 10, "contrast": 15, "saturation": 10, "highlights": -20, "fade": 10, "vignette": 30}),
+                                 ("adjust_sharpen", {"contrast": 10, "sharpen": 40}), ("adjust_clarity9x9", {"contrast": 10, "clarity": 50}),
+                                 ("adjust_everything", {"temperature": 20, "exposure": 10, "contrast": 15, "saturation": 10, "shadows": 20, "sharpen": 40, "clarity": 50, "fade": 10, "vignette": 30})):
+                    desc = vt._adjust_desc(st, H, W)
+                    report(f"{name}/{tag}", timeit(lambda: ops.adjust(x, desc)), npix, bpp)
+                    report(f"{name}/4k_u8bgr", timeit(lambda: ops.adjust(u8, desc)), npix, 6)
                 del u8, u8o, ref
             del x, out
             torch.cuda.empty_cache()
