@@ -141,44 +141,54 @@ k_adjust_box(const float* __restrict__ src, float* __restrict__ dst_scratch, T* 
       d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
     }
     __syncthreads();
-    // 16 x 192 outputs over 256 threads: 12 per thread
-    for (int i = threadIdx.x; i < ADJ_TY * ADJ_TXE; i += 256) {
-      const int ry = i / ADJ_TXE, e = i - ry * ADJ_TXE;
-      const int y = y0 + ry, x = x0 + e / 3, ch = e - (e / 3) * 3;
-      if (y >= A.H || x >= A.W) continue;
-      const float* c0 = tile + (ry + R) * ADJ_SW + e + 3 * R;      // centre element
-      const float xc = *c0;
-      float res = xc;
+    // 16 x 192 outputs = 768 quads of 4 consecutive elements over 256 threads; the four window sums of a quad are independent
+    // dependency chains (each is still summed strictly in avg_pool2d's row-major order), which hides the FADD latency
+    for (int q = threadIdx.x; q < ADJ_TY * (ADJ_TXE / 4); q += 256) {
+      const int ry = q / (ADJ_TXE / 4), e0 = (q - ry * (ADJ_TXE / 4)) * 4;
+      const int y = y0 + ry;
+      if (y >= A.H) continue;
+      const float* c0 = tile + (ry + R) * ADJ_SW + e0 + 3 * R;      // centre of the quad's first element
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (K >= 3) {
-        // avg_pool2d: sum over the window in row-major order, then / (K*K)
-        float acc = 0.0f;
         bool first = true;
         for (int dy = -R; dy <= R; ++dy) {
           const float* rowp = c0 + dy * ADJ_SW;
           for (int dx = -R; dx <= R; ++dx) {
-            const float v = rowp[3 * dx];
-            acc = first ? v : addx(acc, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float v = rowp[3 * dx + j];
+              acc[j] = first ? v : addx(acc[j], v);
+            }
             first = false;
           }
         }
-        const float blur = divx(acc, (float)(K * K));
-        const float detail = subx(xc, blur);
-        if (MODE == 0) {
-          const float* px = c0 - ch;                               // this pixel's r, g, b
-          const float ln = adj_luma(px[0], px[1], px[2]);
-          const float mid = subx(1.0f, clamp01(divx(fabsf(subx(ln, 0.5f)), 0.5f)));
-          const float wgt = addx(0.35f, mulx(mid, 0.65f));
-          res = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j, x = x0 + e / 3, ch = e - (e / 3) * 3;
+        if (x >= A.W) continue;
+        const float xc = c0[j];
+        float res = xc;
+        if (K >= 3) {
+          const float blur = divx(acc[j], (float)(K * K));            // avg_pool2d: sum / (K*K)
+          const float detail = subx(xc, blur);
+          if (MODE == 0) {
+            const float* px = c0 + j - ch;                             // this pixel's r, g, b
+            const float ln = adj_luma(px[0], px[1], px[2]);
+            const float mid = subx(1.0f, clamp01(divx(fabsf(subx(ln, 0.5f)), 0.5f)));
+            const float wgt = addx(0.35f, mulx(mid, 0.65f));
+            res = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
+          } else {
+            res = addx(xc, mulx(mulx(detail, A.sharpen), 5.0f));               // nchw + fine_detail * sharpen * 5.0
+          }
+        }   // K < 3 (frames narrower than 3 pixels): the reference's blur returns x itself, detail == 0, result == x
+        const int64_t o = (((int64_t)frame * A.H + y) * A.W + x) * 3;
+        if (LAST) {
+          const float m = vignette_mask(A, x, y);
+          out[o + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res, m));
         } else {
-          res = addx(xc, mulx(mulx(detail, A.sharpen), 5.0f));               // nchw + fine_detail * sharpen * 5.0
+          dst_scratch[o + ch] = res;
         }
-      }   // K < 3 (frames narrower than 3 pixels): the reference's blur returns x itself, detail == 0, result == x
-      const int64_t o = (((int64_t)frame * A.H + y) * A.W + x) * 3;
-      if (LAST) {
-        const float m = vignette_mask(A, x, y);
-        out[o + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res, m));
-      } else {
-        dst_scratch[o + ch] = res;
       }
     }
     __syncthreads();
