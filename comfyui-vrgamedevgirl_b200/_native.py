@@ -74,6 +74,17 @@ class AdjustDesc(ctypes.Structure):
     ]
 
 
+class ResizeDesc(ctypes.Structure):
+    """struct vrgdg_resize_desc (include/vrgdg_b200.h)."""
+
+    _fields_ = [
+        ("mode", ctypes.c_int32),
+        ("src_x0", ctypes.c_int32), ("src_y0", ctypes.c_int32), ("src_w", ctypes.c_int32), ("src_h", ctypes.c_int32),
+        ("res_w", ctypes.c_int32), ("res_h", ctypes.c_int32),
+        ("off_x", ctypes.c_int32), ("off_y", ctypes.c_int32),
+    ]
+
+
 _vp, _i, _i64, _u64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -99,6 +110,8 @@ SIGNATURES = {
     "vrgdg_chain_lab_moments": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp, _i64, _vp]),
     "vrgdg_adjust_scratch_bytes": (_i64, [_i, _i, _i, ctypes.POINTER(AdjustDesc)]),
     "vrgdg_adjust": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(AdjustDesc), _vp, _vp, _vp, _i64, _vp]),
+    "vrgdg_resize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ResizeDesc), _vp]),
+    "vrgdg_blend": (_i, [_vp, _vp, _vp, _i64, _i, _f, _f, _vp]),
     "vrgdg_u8bgr_to_rgb": (_i, [_vp, _vp, _i64, _i, _vp]),
     "vrgdg_rgb_to_u8bgr": (_i, [_vp, _vp, _i64, _i, _vp]),
 }

@@ -3,6 +3,7 @@
 #include "../../include/vrgdg_b200.h"
 #include "vrgdg_kernels.cuh"
 #include "vrgdg_adjust.cuh"
+#include "vrgdg_resize.cuh"
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
@@ -484,6 +485,51 @@ int vrgdg_adjust(const void* in, void* out, int B, int H, int W, int dtype, cons
   cudaError_t e = DISPATCH_DTYPE(dtype, AJ);
 #undef AJ
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_adjust");
+  return VRGDG_OK;
+}
+
+int vrgdg_resize(const void* in, void* out, int B, int Hs, int Ws, int channels, int Ht, int Wt, int dtype,
+                 const vrgdg_resize_desc* d, void* stream) {
+  if (!d) return fail(VRGDG_E_INVALID, "vrgdg_resize: null descriptor");
+  if (!dtype_ok(dtype) || dtype == VRGDG_U8BGR) return fail(VRGDG_E_INVALID, "vrgdg_resize: float dtype expected, got %d", dtype);
+  if (B < 0 || Hs < 0 || Ws < 0 || Ht < 0 || Wt < 0) return fail(VRGDG_E_INVALID, "vrgdg_resize: negative shape");
+  if (channels != 3 && channels != 4) return fail(VRGDG_E_INVALID, "vrgdg_resize: channels must be 3 or 4, got %d", channels);
+  if (d->mode < VRGDG_RESIZE_NEAREST || d->mode > VRGDG_RESIZE_AREA) return fail(VRGDG_E_INVALID, "vrgdg_resize: unknown mode %d", d->mode);
+  if ((int64_t)B * Ht * Wt == 0) return VRGDG_OK;
+  if (!in || !out) return fail(VRGDG_E_INVALID, "vrgdg_resize: null pointer");
+  if (in == out) return fail(VRGDG_E_INVALID, "vrgdg_resize: in-place resampling is not supported");
+  if (d->src_w < 1 || d->src_h < 1 || d->src_x0 < 0 || d->src_y0 < 0 || (int64_t)d->src_x0 + d->src_w > Ws ||
+      (int64_t)d->src_y0 + d->src_h > Hs)
+    return fail(VRGDG_E_INVALID, "vrgdg_resize: ROI %d,%d %dx%d outside %dx%d frames", d->src_x0, d->src_y0, d->src_w, d->src_h, Ws, Hs);
+  if (d->res_w < 1 || d->res_h < 1) return fail(VRGDG_E_INVALID, "vrgdg_resize: resampled size %dx%d", d->res_w, d->res_h);
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  ResizeParams R;
+  R.B = B; R.Hs = Hs; R.Ws = Ws; R.Cs = channels; R.Ht = Ht; R.Wt = Wt; R.mode = d->mode;
+  R.x0 = d->src_x0; R.y0 = d->src_y0; R.sw = d->src_w; R.sh = d->src_h; R.rw = d->res_w; R.rh = d->res_h;
+  R.ox = d->off_x; R.oy = d->off_y;
+  R.scale_x = (float)d->src_w / (float)d->res_w;
+  R.scale_y = (float)d->src_h / (float)d->res_h;
+#define RZ(T) launch_resize<T>(in, out, R, ctx)
+  cudaError_t e = (dtype == VRGDG_F32) ? RZ(float) : ((dtype == VRGDG_F16) ? RZ(__half) : RZ(__nv_bfloat16));
+#undef RZ
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_resize");
+  return VRGDG_OK;
+}
+
+int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, float weight_a, float weight_b, void* stream) {
+  if (!dtype_ok(dtype) || dtype == VRGDG_U8BGR) return fail(VRGDG_E_INVALID, "vrgdg_blend: float dtype expected, got %d", dtype);
+  if (n < 0) return fail(VRGDG_E_INVALID, "vrgdg_blend: negative element count");
+  if (n == 0) return VRGDG_OK;
+  if (!a || !b || !out) return fail(VRGDG_E_INVALID, "vrgdg_blend: null pointer");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+#define BL(T) launch_blend<T>(a, b, out, n, weight_a, weight_b, ctx)
+  cudaError_t e = (dtype == VRGDG_F32) ? BL(float) : ((dtype == VRGDG_F16) ? BL(__half) : BL(__nv_bfloat16));
+#undef BL
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_blend");
   return VRGDG_OK;
 }
 

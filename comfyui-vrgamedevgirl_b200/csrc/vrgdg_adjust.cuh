@@ -104,95 +104,131 @@ k_adjust_point(const T* __restrict__ in, T* __restrict__ out, float* __restrict_
 }
 
 // ---- stage C (MODE 0, reflect pad, k x k) or S (MODE 1, replicate pad, 3 x 3) on an fp32 RGB scratch frame ----------------------
-// tile = 16 rows x 64 pixels in shared memory; each thread sums the K x K window of its element sequentially in avg_pool2d's
-// row-major order (that order, not a separable sum, is what makes the result bit-identical).
-constexpr int ADJ_TY = 16, ADJ_TXP = 64, ADJ_TXE = ADJ_TXP * 3, ADJ_RMAX = 4;
-constexpr int ADJ_SW = ADJ_TXE + 6 * ADJ_RMAX;        // 216 floats per tile row
+// tile = 16 rows x 64 pixels (+ a fixed 4-pixel apron left and right, R rows above and below) in shared memory.  Each of the 256
+// threads owns 4 pixels = 12 consecutive elements of one row: per window row it pulls the 12 + 2*PAD elements it needs with
+// 128-bit shared loads (conflict-free: a quarter warp's 8 x 16 B land in 32 distinct banks) and feeds 12 independent window sums,
+// each strictly in avg_pool2d's row-major order (that order, not a separable sum, is what makes the result bit-identical).
+// Per output element and window row: 1/12 .. 3/4 of a shared load instead of K, so the kernel is FADD-issue bound.
+constexpr int ADJ_TY = 16, ADJ_TXP = 64, ADJ_TXE = ADJ_TXP * 3, ADJ_RMAX = 4, ADJ_APRON = 4;
+constexpr int ADJ_SW = ADJ_TXE + 6 * ADJ_APRON;       // 216 floats per tile row
 constexpr int ADJ_SH = ADJ_TY + 2 * ADJ_RMAX;         // 24 rows
 
-template <typename T, int MODE, bool LAST>
+template <typename T, int MODE, bool LAST, int K>
 __global__ void __launch_bounds__(256)
 k_adjust_box(const float* __restrict__ src, float* __restrict__ dst_scratch, T* __restrict__ out, AdjustParams A, int tiles_x, int tiles_y) {
   constexpr bool BGR = Io<T>::BGR;
-  __shared__ float tile[ADJ_SH * ADJ_SW];
-  const int R = (MODE == 0) ? A.kbox / 2 : 1, K = 2 * R + 1;
+  constexpr int R = K / 2;
+  constexpr int PAD = ((3 * R + 3) / 4) * 4;           // elements left of the thread's first one, rounded up to a 16-byte boundary
+  constexpr int NV = (12 + 2 * PAD) / 4;               // float4 loads per window row
+  __shared__ __align__(16) float tile[ADJ_SH * ADJ_SW];
   const int RW = A.W * 3;
   const int tiles_per_frame = tiles_x * tiles_y;
   const int total = A.B * tiles_per_frame;
+  const int ry = threadIdx.x >> 4, e0 = (threadIdx.x & 15) * 12;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int frame = t / tiles_per_frame, rem = t - frame * tiles_per_frame;
     const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     const int y0 = ty * ADJ_TY, x0 = tx * ADJ_TXP;
     const float* fbase = src + (int64_t)frame * A.H * RW;
-    // cooperative load with padding by index mapping (reflect: -i -> i, n-1+i -> n-1-i ; replicate: clamp)
-    const int rows = ADJ_TY + 2 * R, colsp = ADJ_TXP + 2 * R;
+    // cooperative load with padding by index mapping (reflect: -i -> i, n-1+i -> n-1-i ; replicate: clamp); apron columns
+    // further out than R are never read by a window and only need an in-range address
+    constexpr int rows = ADJ_TY + 2 * R, colsp = ADJ_TXP + 2 * ADJ_APRON;
     for (int i = threadIdx.x; i < rows * colsp; i += 256) {
       const int rr = i / colsp, cp = i - rr * colsp;
-      int y = y0 - R + rr, x = x0 - R + cp;
+      int y = y0 - R + rr, x = x0 - ADJ_APRON + cp;
       if (MODE == 0) {
         y = y < 0 ? -y : (y >= A.H ? 2 * (A.H - 1) - y : y);
         x = x < 0 ? -x : (x >= A.W ? 2 * (A.W - 1) - x : x);
-        y = max(0, min(y, A.H - 1)); x = max(0, min(x, A.W - 1));      // tiles beyond the image edge (masked later)
-      } else {
-        y = max(0, min(y, A.H - 1)); x = max(0, min(x, A.W - 1));
       }
+      y = max(0, min(y, A.H - 1)); x = max(0, min(x, A.W - 1));
       const float* s = fbase + ((int64_t)y * A.W + x) * 3;
       float* d = tile + rr * ADJ_SW + cp * 3;
       d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
     }
     __syncthreads();
-    // 16 x 192 outputs = 768 quads of 4 consecutive elements over 256 threads; the four window sums of a quad are independent
-    // dependency chains (each is still summed strictly in avg_pool2d's row-major order), which hides the FADD latency
-    for (int q = threadIdx.x; q < ADJ_TY * (ADJ_TXE / 4); q += 256) {
-      const int ry = q / (ADJ_TXE / 4), e0 = (q - ry * (ADJ_TXE / 4)) * 4;
-      const int y = y0 + ry;
-      if (y >= A.H) continue;
-      const float* c0 = tile + (ry + R) * ADJ_SW + e0 + 3 * R;      // centre of the quad's first element
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (K >= 3) {
-        bool first = true;
-        for (int dy = -R; dy <= R; ++dy) {
-          const float* rowp = c0 + dy * ADJ_SW;
-          for (int dx = -R; dx <= R; ++dx) {
+    const int y = y0 + ry;
+    if (y < A.H) {
+      const float* c0 = tile + (ry + R) * ADJ_SW + 3 * ADJ_APRON + e0;   // the thread's first element (16-byte aligned)
+      float acc[12];
+      float ctr[12];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float v = rowp[3 * dx + j];
-              acc[j] = first ? v : addx(acc[j], v);
-            }
-            first = false;
+      for (int dy = -R; dy <= R; ++dy) {
+        float v[NV * 4];
+        const float4* rowp = reinterpret_cast<const float4*>(c0 + dy * ADJ_SW - PAD);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const float4 q = rowp[k];
+          v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        }
+        if (dy == 0) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) ctr[j] = v[PAD + j];
+        }
+#pragma unroll
+        for (int dx = -R; dx <= R; ++dx) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const float w = v[PAD + j + 3 * dx];
+            acc[j] = (dy == -R && dx == -R) ? w : addx(acc[j], w);
           }
         }
       }
+      float res[12];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = e0 + j, x = x0 + e / 3, ch = e - (e / 3) * 3;
-        if (x >= A.W) continue;
-        const float xc = c0[j];
-        float res = xc;
+      for (int j = 0; j < 12; ++j) {
+        const float xc = ctr[j];
+        res[j] = xc;
         if (K >= 3) {
-          const float blur = divx(acc[j], (float)(K * K));            // avg_pool2d: sum / (K*K)
+          const float blur = divx(acc[j], (float)(K * K));              // avg_pool2d: sum / (K*K)
           const float detail = subx(xc, blur);
           if (MODE == 0) {
-            const float* px = c0 + j - ch;                             // this pixel's r, g, b
-            const float ln = adj_luma(px[0], px[1], px[2]);
+            const int p = (j / 3) * 3;                                   // this pixel's r, g, b
+            const float ln = adj_luma(ctr[p], ctr[p + 1], ctr[p + 2]);
             const float mid = subx(1.0f, clamp01(divx(fabsf(subx(ln, 0.5f)), 0.5f)));
             const float wgt = addx(0.35f, mulx(mid, 0.65f));
-            res = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
+            res[j] = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
           } else {
-            res = addx(xc, mulx(mulx(detail, A.sharpen), 5.0f));               // nchw + fine_detail * sharpen * 5.0
+            res[j] = addx(xc, mulx(mulx(detail, A.sharpen), 5.0f));               // nchw + fine_detail * sharpen * 5.0
           }
         }   // K < 3 (frames narrower than 3 pixels): the reference's blur returns x itself, detail == 0, result == x
-        const int64_t o = (((int64_t)frame * A.H + y) * A.W + x) * 3;
-        if (LAST) {
-          const float m = vignette_mask(A, x, y);
-          out[o + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res, m));
-        } else {
-          dst_scratch[o + ch] = res;
+      }
+      const int xq = x0 + (threadIdx.x & 15) * 4;
+      const int64_t o = (((int64_t)frame * A.H + y) * A.W + xq) * 3;
+      if (!LAST && xq + 3 < A.W && (A.W & 3) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dst_scratch + o);
+        d4[0] = make_float4(res[0], res[1], res[2], res[3]);
+        d4[1] = make_float4(res[4], res[5], res[6], res[7]);
+        d4[2] = make_float4(res[8], res[9], res[10], res[11]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const int px = j / 3, ch = j - px * 3;
+          if (xq + px >= A.W) continue;
+          if (LAST) {
+            const float m = vignette_mask(A, xq + px, y);
+            out[o + px * 3 + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res[j], m));
+          } else {
+            dst_scratch[o + j] = res[j];
+          }
         }
       }
     }
     __syncthreads();
   }
+}
+
+template <typename T, int MODE, bool LAST>
+cudaError_t launch_adjust_box(int K, int grid, const float* src, float* dst, T* out, const AdjustParams& A, int tiles_x, int tiles_y,
+                              cudaStream_t stream) {
+  switch (K) {
+    case 9: k_adjust_box<T, MODE, LAST, 9><<<grid, 256, 0, stream>>>(src, dst, out, A, tiles_x, tiles_y); break;
+    case 7: k_adjust_box<T, MODE, LAST, 7><<<grid, 256, 0, stream>>>(src, dst, out, A, tiles_x, tiles_y); break;
+    case 5: k_adjust_box<T, MODE, LAST, 5><<<grid, 256, 0, stream>>>(src, dst, out, A, tiles_x, tiles_y); break;
+    case 3: k_adjust_box<T, MODE, LAST, 3><<<grid, 256, 0, stream>>>(src, dst, out, A, tiles_x, tiles_y); break;
+    default: k_adjust_box<T, MODE, LAST, 1><<<grid, 256, 0, stream>>>(src, dst, out, A, tiles_x, tiles_y); break;
+  }
+  count_launch();
+  return cudaGetLastError();
 }
 
 template <typename T>
@@ -217,16 +253,13 @@ cudaError_t launch_adjust(const void* in, void* out, const AdjustParams& A, int 
   const int tgrid = (int)std::min<int64_t>(tiles, (int64_t)ctx.sms * 8);
   const float* cur = s1;
   if (C) {
-    if (S) k_adjust_box<T, 0, false><<<tgrid, 256, 0, ctx.stream>>>(cur, s2, tout, A, tiles_x, tiles_y);
-    else k_adjust_box<T, 0, true><<<tgrid, 256, 0, ctx.stream>>>(cur, nullptr, tout, A, tiles_x, tiles_y);
-    count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    e = S ? launch_adjust_box<T, 0, false>(A.kbox, tgrid, cur, s2, tout, A, tiles_x, tiles_y, ctx.stream)
+          : launch_adjust_box<T, 0, true>(A.kbox, tgrid, cur, nullptr, tout, A, tiles_x, tiles_y, ctx.stream);
+    if (e != cudaSuccess) return e;
     cur = s2;
   }
   if (S) {
-    k_adjust_box<T, 1, true><<<tgrid, 256, 0, ctx.stream>>>(cur, nullptr, tout, A, tiles_x, tiles_y);
-    count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_adjust_box<T, 1, true>(3, tgrid, cur, nullptr, tout, A, tiles_x, tiles_y, ctx.stream)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

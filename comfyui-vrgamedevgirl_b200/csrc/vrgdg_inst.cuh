@@ -3,6 +3,7 @@
 #include "vrgdg_kernels.cuh"
 #include <algorithm>
 #include "vrgdg_adjust.cuh"
+#include "vrgdg_resize.cuh"
 #include <string.h>
 
 namespace vrgdg {
@@ -152,6 +153,8 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
   template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&); \
   template cudaError_t launch_adjust<T>(const void*, void*, const AdjustParams&, int, float*, float*, const LaunchCtx&);              \
+  template cudaError_t launch_resize<T>(const void*, void*, const ResizeParams&, const LaunchCtx&);                       \
+  template cudaError_t launch_blend<T>(const void*, const void*, void*, int64_t, float, float, const LaunchCtx&);         \
   template void tile_geometry<T>(int, int, int&, int&, int&, int&);
 
 #define VRGDG_INSTANTIATE_CODECS(T)                                                                                       \

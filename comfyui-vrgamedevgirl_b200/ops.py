@@ -204,6 +204,45 @@ def adjust(images, desc):
     return out
 
 
+RESIZE_MODES = {"nearest": 0, "bilinear": 1, "bicubic": 2, "area": 3}
+
+
+def resize(images, out_h, out_w, mode, roi=None, resampled=None, offset=(0, 0)):
+    """Resample roi=(x0, y0, w, h) of images [B,H,W,3|4] to resampled=(w, h) and place it at offset=(x, y) inside a zero-filled,
+    clamped [B,out_h,out_w,3] result (vrgdg_resize; F.interpolate(..., align_corners=False) semantics)."""
+    t = nv.require_cuda(images, "images")
+    if t.ndim != 4 or t.shape[-1] not in (3, 4):
+        raise ValueError("vrgdg_b200: expected frames [B,H,W,3|4], got %s" % (tuple(t.shape),))
+    if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise ValueError("vrgdg_b200: resize needs float frames, got %s" % t.dtype)
+    t = t.contiguous()
+    B, H, W, C = t.shape
+    x0, y0, sw, sh = roi if roi is not None else (0, 0, W, H)
+    rw, rh = resampled if resampled is not None else (out_w, out_h)
+    d = nv.ResizeDesc(RESIZE_MODES[mode], int(x0), int(y0), int(sw), int(sh), int(rw), int(rh), int(offset[0]), int(offset[1]))
+    out = torch.empty((B, int(out_h), int(out_w), 3), dtype=t.dtype, device=t.device)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_resize(nv.ptr(t), nv.ptr(out), B, H, W, C, int(out_h), int(out_w), nv.DTYPE_CODE[t.dtype], ctypes.byref(d),
+                                  nv.stream_ptr(t.device)))
+    return out
+
+
+def blend(a, b, weight_a, weight_b):
+    """clamp(a * weight_a + b * weight_b, 0, 1) (vrgdg_blend)."""
+    ta, tb = nv.require_cuda(a, "a").contiguous(), nv.require_cuda(b, "b").contiguous()
+    if ta.shape != tb.shape or ta.dtype != tb.dtype or ta.device != tb.device:
+        raise ValueError("vrgdg_b200: blend operands differ (%s %s vs %s %s)" % (tuple(ta.shape), ta.dtype, tuple(tb.shape), tb.dtype))
+    if ta.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise ValueError("vrgdg_b200: blend needs float frames, got %s" % ta.dtype)
+    out = torch.empty_like(ta)
+    lib = nv.load_library()
+    with torch.cuda.device(ta.device):
+        nv.check(lib.vrgdg_blend(nv.ptr(ta), nv.ptr(tb), nv.ptr(out), ta.numel(), nv.DTYPE_CODE[ta.dtype], float(weight_a), float(weight_b),
+                                 nv.stream_ptr(ta.device)))
+    return out
+
+
 def u8bgr_to_rgb(frames_u8, dtype=torch.float32):
     """uint8 BGR [..., 3] CUDA -> RGB float (x/255)."""
     if frames_u8.device.type != "cuda" or frames_u8.dtype != torch.uint8 or frames_u8.shape[-1] != 3:

@@ -70,6 +70,7 @@ enum { VRGDG_BORDER_REPLICATE = 0, VRGDG_BORDER_ZERO = 1 };
  *              (_apply_seeded_grain VRGDG_StandaloneVideoEnhancerNodes.py:266-269)
  * Both make the result independent of batch boundaries and of how frames are sharded. */
 enum { VRGDG_SEED_PER_CLIP = 0, VRGDG_SEED_PER_FRAME = 1 };
+enum { VRGDG_RESIZE_NEAREST = 0, VRGDG_RESIZE_BILINEAR = 1, VRGDG_RESIZE_BICUBIC = 2, VRGDG_RESIZE_AREA = 3 };
 
 /* ---- library ---------------------------------------------------------------------------- */
 VRGDG_API int vrgdg_version(void);
@@ -210,6 +211,25 @@ typedef struct vrgdg_adjust_desc {
 VRGDG_API int64_t vrgdg_adjust_scratch_bytes(int B, int H, int W, const vrgdg_adjust_desc* desc);
 VRGDG_API int vrgdg_adjust(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_adjust_desc* desc,
                  const float* xx, const float* yy, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- resize / restore around the enhancer ----------------------------------------------------------
+ * _resize_batch / _restore_batch (VRGDG_VideoEnhanceNodes.py:54-106): F.interpolate(mode, align_corners=False, size=...)
+ * of an RGB ROI, then a crop ("Crop to fill"), zero letterbox bars ("Fit with letterbox") or nothing ("Stretch"), then
+ * clamp(0,1).  The ROI [src_x0, src_x0+src_w) x [src_y0, src_y0+src_h) of in [B,Hs,Ws,channels] (channels 3 or 4, alpha
+ * ignored) is resampled to res_w x res_h; output pixel (x, y) of out [B,Ht,Wt,3] is resampled pixel (x - off_x, y - off_y)
+ * or 0 outside it.  Nearest and area are bit-identical to torch, bilinear / bicubic within fp32 rounding (2e-6). */
+typedef struct vrgdg_resize_desc {
+  int32_t mode;                          /* VRGDG_RESIZE_* */
+  int32_t src_x0, src_y0, src_w, src_h;
+  int32_t res_w, res_h;
+  int32_t off_x, off_y;
+} vrgdg_resize_desc;
+VRGDG_API int vrgdg_resize(const void* in, void* out, int B, int Hs, int Ws, int channels, int Ht, int Wt, int dtype,
+                 const vrgdg_resize_desc* desc, void* stream);
+/* out = clamp(a * weight_a + b * weight_b, 0, 1), one rounding per operation: the restore blend
+ * originals * (1 - strength) + restored * strength (VRGDG_VideoEnhanceNodes.py:408-414).  n = elements. */
+VRGDG_API int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, float weight_a, float weight_b,
+                void* stream);
 
 /* ---- uint8 BGR wire format -------------------------------------------------------------------------
  * _frames_to_tensor / _tensor_to_frames (VRGDG_LUTVideoTools.py:736-752,

@@ -77,3 +77,10 @@ def load_lut_video_helpers(iv=None):
     ns = {"torch": torch, "VRGDG_LUTS": iv.VRGDG_LUTS}
     names = {"_apply_lut_tensor", "_apply_film_grain_tensor", "_normalize_adjust_settings", "_apply_adjust_tensor"}
     return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_LUTVideoTools.py"), names, ns)
+
+
+def load_video_enhance_helpers():
+    """_interpolation / _resize_batch / _restore_batch of VRGDG_VideoEnhanceNodes.py:45-106."""
+    ns = {"torch": torch, "F": F}
+    names = {"_interpolation", "_resize_batch", "_restore_batch"}
+    return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_VideoEnhanceNodes.py"), names, ns)

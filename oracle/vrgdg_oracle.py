@@ -408,6 +408,57 @@ def adjust(image_tensor, settings=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# resize / restore around the enhancer (VRGDG_VideoEnhanceNodes.py:45-106, :408-414)
+# --------------------------------------------------------------------------------------------------
+INTERPOLATIONS = {"Nearest": "nearest", "Bilinear": "bilinear", "Bicubic (recommended)": "bicubic", "Area": "area"}
+
+
+def resize_batch(images, target_width, target_height, fit_mode, resize_method):
+    """_resize_batch, VRGDG_VideoEnhanceNodes.py:54-86."""
+    if images.ndim != 4 or images.shape[0] < 1:
+        raise ValueError("Video Enhance requires a non-empty IMAGE batch.")
+    sh, sw = int(images.shape[1]), int(images.shape[2])
+    tw, th = int(target_width), int(target_height)
+    x = images[..., :3].permute(0, 3, 1, 2)
+    mode = INTERPOLATIONS.get(str(resize_method), "bicubic")
+    kw = {"mode": mode}
+    if mode in ("bilinear", "bicubic"):
+        kw["align_corners"] = False
+    if fit_mode == "Stretch to dimensions":
+        res = F.interpolate(x, size=(th, tw), **kw)
+    else:
+        scale = max(tw / sw, th / sh) if fit_mode == "Crop to fill" else min(tw / sw, th / sh)
+        rw, rh = max(1, int(round(sw * scale))), max(1, int(round(sh * scale)))
+        r = F.interpolate(x, size=(rh, rw), **kw)
+        if fit_mode == "Crop to fill":
+            left, top = max(0, (rw - tw) // 2), max(0, (rh - th) // 2)
+            res = r[:, :, top:top + th, left:left + tw]
+        else:
+            pl = max(0, (tw - rw) // 2)
+            pt = max(0, (th - rh) // 2)
+            res = F.pad(r, (pl, max(0, tw - rw - pl), pt, max(0, th - rh - pt)), value=0.0)
+    return res.permute(0, 2, 3, 1).clamp(0, 1)
+
+
+def restore_batch(images, source_width, source_height, fit_mode, resize_method):
+    """_restore_batch, VRGDG_VideoEnhanceNodes.py:89-106."""
+    if fit_mode != "Fit with letterbox (preserve all)":
+        return resize_batch(images, source_width, source_height, "Stretch to dimensions", resize_method)
+    wh, ww = int(images.shape[1]), int(images.shape[2])
+    scale = min(ww / source_width, wh / source_height)
+    cw = min(ww, max(1, int(round(source_width * scale))))
+    ch = min(wh, max(1, int(round(source_height * scale))))
+    left, top = max(0, (ww - cw) // 2), max(0, (wh - ch) // 2)
+    return resize_batch(images[:, top:top + ch, left:left + cw, :], source_width, source_height, "Stretch to dimensions", resize_method)
+
+
+def restore_blend(originals, restored, strength):
+    """VRGDG_VideoEnhanceNodes.py:408-414: lerp of the restored frames over the originals, clamp."""
+    s = float(strength)
+    return (originals * (1.0 - s) + restored * s).clamp(0, 1)
+
+
+# --------------------------------------------------------------------------------------------------
 # uint8 BGR wire format
 # --------------------------------------------------------------------------------------------------
 def frames_to_tensor(frames_bgr_u8):

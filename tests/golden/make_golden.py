@@ -207,6 +207,23 @@ def main():
     save("adjust", **adj)
     meta["adjust_cases"] = ADJ_CASES
 
+    # ---- resize / restore (VRGDG_VideoEnhanceNodes.py) -------------------------------------------------------------------------
+    ve = RH.load_video_enhance_helpers()
+    xr = natural_frames(2, 54, 96, seed=85)
+    rz = {"x": xr}
+    RESIZE_CASES = []
+    for method in ("Nearest", "Bilinear", "Bicubic (recommended)", "Area"):
+        for fit, (tw, th) in (("Stretch to dimensions", (160, 72)), ("Crop to fill", (64, 64)), ("Fit with letterbox (preserve all)", (80, 80)),
+                              ("Stretch to dimensions", (40, 30))):
+            key = "%s|%s|%dx%d" % (method.split()[0], fit.split()[0], tw, th)
+            RESIZE_CASES.append([key, method, fit, tw, th])
+            rz[key] = ve["_resize_batch"](xr, tw, th, fit, method)
+    up = ve["_resize_batch"](xr, 80, 80, "Fit with letterbox (preserve all)", "Bicubic (recommended)")
+    rz["restore_letterbox"] = ve["_restore_batch"](up, 96, 54, "Fit with letterbox (preserve all)", "Bicubic (recommended)")
+    rz["restore_stretch"] = ve["_restore_batch"](up, 96, 54, "Stretch to dimensions", "Bilinear")
+    save("resize", **rz)
+    meta["resize_cases"] = RESIZE_CASES
+
     # ---- node API surface ---------------------------------------------------------------------------------------------
     api = {}
     classes = dict(nodes)

@@ -609,3 +609,79 @@ def test_adjust_full_size_properties(pkg, cuda_device, oracle):
     a = pkg.ops.adjust(u8, vt._adjust_desc(st, 1080, 1920))
     b = pkg.ops.rgb_to_u8bgr(pkg.ops.adjust(pkg.ops.u8bgr_to_rgb(u8), vt._adjust_desc(st, 1080, 1920)))
     assert a.dtype == torch.uint8 and torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# resize / restore around the enhancer: VRGDG_VideoEnhanceNodes.py:54-106, :404-418
+# ------------------------------------------------------------------------------------------------------
+RESIZE_TOL = 2e-6      # bilinear / bicubic: fp32 rounding (ATen's own CPU kernels differ by this much between thread counts)
+
+
+def test_resize_batch_all_modes_vs_reference(pkg, cuda_device, meta):
+    import importlib
+    ve = importlib.import_module("comfyui-vrgamedevgirl_b200.video_enhance")
+    g = load_golden("resize")
+    x = t(g["x"])
+    for key, method, fit, tw, th in meta["resize_cases"]:
+        before = pkg._native.launch_count()
+        out = ve._resize_batch(x, tw, th, fit, method)
+        assert pkg._native.launch_count() == before + 1, key          # interpolate + crop / pad + clamp: one launch
+        ref = t(g[key])
+        assert out.shape == ref.shape and out.device.type == "cpu", key
+        if method in ("Nearest", "Area"):
+            assert torch.equal(out, ref), key
+        else:
+            assert maxdiff(out, ref) <= RESIZE_TOL, (key, maxdiff(out, ref))
+    up = t(g["Bicubic|Fit|80x80"])
+    assert maxdiff(ve._restore_batch(up, 96, 54, "Fit with letterbox (preserve all)", "Bicubic (recommended)"), t(g["restore_letterbox"])) <= RESIZE_TOL
+    assert maxdiff(ve._restore_batch(up, 96, 54, "Stretch to dimensions", "Bilinear"), t(g["restore_stretch"])) <= RESIZE_TOL
+    # RGBA input: alpha is dropped like images[..., :3]; unknown method names fall back to bicubic (:45-51)
+    rgba = torch.cat([x, torch.ones_like(x[..., :1])], dim=-1)
+    assert torch.equal(ve._resize_batch(rgba, 160, 72, "Stretch to dimensions", "Nearest"), t(g["Nearest|Stretch|160x72"]))
+    assert torch.equal(ve._resize_batch(x, 160, 72, "Stretch to dimensions", "???"), ve._resize_batch(x, 160, 72, "Stretch to dimensions", "Bicubic (recommended)"))
+    with pytest.raises(ValueError):
+        ve._resize_batch(x[0], 10, 10, "Stretch to dimensions", "Nearest")
+    # half precision frames: same geometry, fp16 rounding of the result
+    h = ve._resize_batch(x.to(cuda_device).half(), 160, 72, "Stretch to dimensions", "Bilinear")
+    assert h.dtype == torch.float16 and h.device.type == "cuda"
+    assert maxdiff(h.float().cpu(), t(g["Bilinear|Stretch|160x72"])) <= 1.5e-3
+
+
+def test_resize_full_size_vs_oracle_and_properties(pkg, cuda_device, oracle):
+    """720p -> 1080p and back (the enhancer's prepare / restore shapes), against the oracle on whole frames (~1 s CPU), plus
+    size-independent properties: identity at equal size, letterbox bars are exact zeros, restore(crop ROI) == resize of the crop."""
+    import importlib
+    ve = importlib.import_module("comfyui-vrgamedevgirl_b200.video_enhance")
+    x = natural_frames(2, 720, 1280, seed=93) * 1.1 - 0.05
+    for method in ("Nearest", "Bilinear", "Bicubic (recommended)", "Area"):
+        up = ve._resize_batch(x, 1920, 1088, "Crop to fill", method)
+        ref = oracle.resize_batch(x, 1920, 1088, "Crop to fill", method)
+        assert up.shape == ref.shape == (2, 1088, 1920, 3)
+        assert (torch.equal(up, ref) if method in ("Nearest", "Area") else maxdiff(up, ref) <= RESIZE_TOL), method
+        down = ve._restore_batch(up, 1280, 720, "Crop to fill", method)
+        refd = oracle.restore_batch(ref, 1280, 720, "Crop to fill", method)
+        assert (torch.equal(down, refd) if method == "Nearest" else maxdiff(down, refd) <= 2 * RESIZE_TOL), method
+        same = ve._resize_batch(x, 1280, 720, "Stretch to dimensions", method)
+        assert maxdiff(same, x.clamp(0, 1)) <= (0 if method in ("Nearest", "Area") else 1e-6), method
+    lb = ve._resize_batch(x, 1024, 1024, "Fit with letterbox (preserve all)", "Bicubic (recommended)")
+    assert lb.shape == (2, 1024, 1024, 3)
+    assert float(lb[:, :224].abs().max()) == 0.0 and float(lb[:, 800:].abs().max()) == 0.0       # 1024x576 content, 224-row bars
+    assert maxdiff(lb, oracle.resize_batch(x, 1024, 1024, "Fit with letterbox (preserve all)", "Bicubic (recommended)")) <= RESIZE_TOL
+    back = ve._restore_batch(lb, 1280, 720, "Fit with letterbox (preserve all)", "Bicubic (recommended)")
+    assert maxdiff(back, ve._resize_batch(lb[:, 224:800].contiguous(), 1280, 720, "Stretch to dimensions", "Bicubic (recommended)")) == 0.0
+
+
+def test_restore_frames_blend_bit_exact(pkg, cuda_device, oracle):
+    import importlib
+    ve = importlib.import_module("comfyui-vrgamedevgirl_b200.video_enhance")
+    orig = natural_frames(5, 54, 96, seed=95) * 1.2 - 0.1
+    enh = natural_frames(3, 54, 96, seed=96)                                   # sampler returned 2 frames fewer, same size
+    out = ve.restore_frames(orig, enh, 96, 54, "Stretch to dimensions", "Nearest", 0.65)
+    ref = orig.clone()
+    ref[:3] = orig[:3] * (1.0 - 0.65) + oracle.restore_batch(enh, 96, 54, "Stretch to dimensions", "Nearest") * 0.65
+    assert torch.equal(out, ref.clamp(0, 1))                                   # :410-418, tail frames keep the (clamped) original
+    assert torch.equal(out[3:], orig[3:].clamp(0, 1))
+    a, b = orig[:3].to(cuda_device), enh.to(cuda_device)
+    assert torch.equal(pkg.ops.blend(a, b, 1.0, 0.0), a.clamp(0, 1)) and torch.equal(pkg.ops.blend(a, b, 0.0, 1.0), b)
+    with pytest.raises(ValueError):
+        pkg.ops.blend(a, b[:2], 0.5, 0.5)

@@ -180,3 +180,25 @@ def test_adjust_settings_normalisation_and_descriptor(pkg, oracle):
     import ctypes
     assert lib.vrgdg_adjust_scratch_bytes(2, 10, 20, ctypes.byref(d)) == 2 * 10 * 20 * 3 * 4
     assert lib.vrgdg_adjust_scratch_bytes(2, 10, 20, ctypes.byref(vt._adjust_desc({}, 10, 20))) == 0
+
+
+def test_resize_plan_matches_the_reference_shapes(pkg, oracle):
+    """video_enhance._resize_plan / _output_size (host arithmetic of _resize_batch :66-85): for random sizes the planned output
+    shape, content rectangle and offsets equal what the reference's interpolate + slice / pad produce (oracle, nearest, tiny)."""
+    import importlib
+    ve = importlib.import_module("comfyui-vrgamedevgirl_b200.video_enhance")
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        sw, sh, tw, th = (int(v) for v in rng.integers(1, 40, size=4))
+        x = torch.ones(1, sh, sw, 3)
+        for fit in ("Stretch to dimensions", "Crop to fill", "Fit with letterbox (preserve all)"):
+            ref = oracle.resize_batch(x, tw, th, fit, "Nearest")
+            res, off = ve._resize_plan(sw, sh, tw, th, fit)
+            ow, oh = ve._output_size(res, off, tw, th, fit)
+            assert (oh, ow) == tuple(ref.shape[1:3]), (sw, sh, tw, th, fit)
+            inside = torch.zeros(oh, ow)
+            inside[max(off[1], 0):max(off[1], 0) + min(res[1], oh), max(off[0], 0):max(off[0], 0) + min(res[0], ow)] = 1
+            assert torch.equal(inside, ref[0, :, :, 0]), (sw, sh, tw, th, fit)
+    assert ve._interpolation("Area") == "area" and ve._interpolation("nope") == "bicubic"
+    with pytest.raises(ValueError):
+        ve._resize_batch(torch.zeros(0, 4, 4, 3), 8, 8, "Stretch to dimensions", "Nearest")

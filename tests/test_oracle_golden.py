@@ -108,6 +108,21 @@ def test_adjust_restatement_bit_exact(oracle):
         oracle.normalize_adjust_settings({}), enabled=False, fade=100.0)
 
 
+def test_resize_restatement_bit_exact(oracle):
+    """_resize_batch / _restore_batch (VRGDG_VideoEnhanceNodes.py:54-106): every interpolation x fit mode, torch on both sides."""
+    g = load_golden("resize")
+    with open(os.path.join(GOLDEN, "reference_meta.json"), encoding="utf-8") as fh:
+        cases = json.load(fh)["resize_cases"]
+    assert len(cases) == 16 and {c[1] for c in cases} == set(oracle.INTERPOLATIONS)
+    for key, method, fit, tw, th in cases:
+        assert torch.equal(oracle.resize_batch(t(g["x"]), tw, th, fit, method), t(g[key])), key
+    up = t(g["Bicubic|Fit|80x80"])
+    assert torch.equal(oracle.restore_batch(up, 96, 54, "Fit with letterbox (preserve all)", "Bicubic (recommended)"), t(g["restore_letterbox"]))
+    assert torch.equal(oracle.restore_batch(up, 96, 54, "Stretch to dimensions", "Bilinear"), t(g["restore_stretch"]))
+    with pytest.raises(ValueError):
+        oracle.resize_batch(t(g["x"])[0], 8, 8, "Stretch to dimensions", "Nearest")
+
+
 def test_u8_restatement(oracle):
     g = load_golden("u8")
     assert torch.equal(oracle.frames_to_tensor(g["bgr"]), t(g["rgb_float"]))

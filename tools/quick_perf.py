@@ -99,5 +99,27 @@ def main():
             torch.cuda.empty_cache()
 
 
+def resize_lines():
+    """resize / restore (video_enhance): GPx/s counts OUTPUT pixels; bytes = source + output frames."""
+    for dt, tag in ((torch.float32, "f32"), (torch.float16, "f16")):
+        small = natural_frames(8, 1080, 1920, seed=3, dtype=dt, device=dev)
+        big = natural_frames(2, 2160, 3840, seed=4, dtype=dt, device=dev)
+        es = small.element_size()
+        for mode in ("nearest", "bilinear", "bicubic", "area"):
+            nout = 8 * 2160 * 3840
+            ms = timeit(lambda: ops.resize(small, 2160, 3840, mode), iters=6, warm=2)
+            report(f"resize_{mode}_up2x/8x1080p_{tag}", ms, nout, 3 * es * 1.25)
+            nout = 2 * 1080 * 1920
+            ms = timeit(lambda: ops.resize(big, 1080, 1920, mode), iters=6, warm=2)
+            report(f"resize_{mode}_down2x/2x4k_{tag}", ms, nout, 3 * es * 5)
+        a = natural_frames(4, 2160, 3840, seed=5, dtype=dt, device=dev)
+        b = natural_frames(4, 2160, 3840, seed=6, dtype=dt, device=dev)
+        report(f"restore_blend/4x4k_{tag}", timeit(lambda: ops.blend(a, b, 0.35, 0.65)), 4 * 2160 * 3840, 9 * es)
+        del small, big, a, b
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
-    main()
+    if "--resize-only" not in sys.argv:
+        main()
+    resize_lines()
