@@ -2,8 +2,10 @@
 // Validates arguments, builds TMA tensor maps, dispatches on dtype, never throws.
 #include "../../include/vrgdg_b200.h"
 #include "vrgdg_kernels.cuh"
+#include <cmath>
 #include "vrgdg_adjust.cuh"
 #include "vrgdg_resize.cuh"
+#include "vrgdg_lanczos.cuh"
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
@@ -530,6 +532,80 @@ int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, f
   cudaError_t e = (dtype == VRGDG_F32) ? BL(float) : ((dtype == VRGDG_F16) ? BL(__half) : BL(__nv_bfloat16));
 #undef BL
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_blend");
+  return VRGDG_OK;
+}
+
+// OpenCV's interpolateLanczos4 (imgproc/resize.cpp), restated: note that x + 3 and x + 3 - i are FLOAT sums before the promotion
+// to double, and the accumulation / normalisation of the eight weights is float as well
+static void lanczos4_weights(float x, float* coeffs) {
+  static const double s45 = 0.70710678118654752440084436210485;
+  static const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double pi = 3.1415926535897932384626433832795;
+  float sum = 0.f;
+  const float x3 = x + 3.f;
+  const double y0 = (double)(-x3) * pi * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+  for (int i = 0; i < 8; ++i) {
+    const float d = x3 - (float)i;
+    if (std::fabs(d) >= 1e-6f) {
+      const double y = (double)(-d) * pi * 0.25;
+      coeffs[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    } else {
+      coeffs[i] = 1e30f;                                   // the tap that sits exactly on a source sample takes all the weight
+    }
+    sum += coeffs[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; ++i) coeffs[i] *= sum;
+}
+
+int vrgdg_lanczos4_tables(int src_size, int dst_size, int32_t* ofs, int16_t* coef) {
+  if (src_size < 1 || dst_size < 1) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_tables: sizes %d -> %d", src_size, dst_size);
+  if (!ofs || !coef) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_tables: null pointer");
+  const double inv_scale = (double)dst_size / (double)src_size;
+  const volatile double scale = 1.0 / inv_scale;            // cv::resize: scale_x = 1. / inv_scale_x (volatile: no fused multiply-add below)
+  for (int d = 0; d < dst_size; ++d) {
+    const volatile double prod = ((double)d + 0.5) * scale;
+    float fx = (float)(prod - 0.5);
+    const int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    ofs[d] = sx;
+    float w[8];
+    lanczos4_weights(fx, w);
+    for (int k = 0; k < 8; ++k) {
+      const long r = lrintf(w[k] * 2048.f);                  // saturate_cast<short>(cvRound(.)), round half to even
+      coef[(size_t)d * 8 + k] = (int16_t)(r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+    }
+  }
+  return VRGDG_OK;
+}
+
+int64_t vrgdg_lanczos4_scratch_bytes(int B, int Hs, int Wd) {
+  if (B < 0 || Hs < 0 || Wd < 0) return 0;
+  return (int64_t)B * Hs * Wd * 3 * (int64_t)sizeof(int32_t);
+}
+
+int vrgdg_lanczos4_resize_u8(const uint8_t* in, uint8_t* out, int B, int Hs, int Ws, int Hd, int Wd, const int32_t* xofs,
+                             const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, void* scratch, int64_t scratch_bytes,
+                             void* stream) {
+  if (B < 0 || Hs < 0 || Ws < 0 || Hd < 0 || Wd < 0) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_resize_u8: negative shape");
+  if ((int64_t)B * Hd * Wd == 0) return VRGDG_OK;
+  if (Hs < 1 || Ws < 1) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_resize_u8: empty source frames");
+  if (!in || !out || !xofs || !xcoef || !yofs || !ycoef) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_resize_u8: null pointer");
+  if (in == out) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_resize_u8: in-place resampling is not supported");
+  if ((int64_t)Wd * 3 > 0x7FFFFFFF || (int64_t)Ws * 3 > 0x7FFFFFFF) return fail(VRGDG_E_UNSUPPORTED, "vrgdg_lanczos4_resize_u8: rows too long");
+  const int64_t need = vrgdg_lanczos4_scratch_bytes(B, Hs, Wd);
+  if (!scratch || scratch_bytes < need) return fail(VRGDG_E_INVALID, "vrgdg_lanczos4_resize_u8: scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)need);
+  if ((reinterpret_cast<uintptr_t>(scratch) & 15u) || (reinterpret_cast<uintptr_t>(xcoef) & 15u) || (reinterpret_cast<uintptr_t>(ycoef) & 15u))
+    return fail(VRGDG_E_ALIGN, "vrgdg_lanczos4_resize_u8: scratch and weight tables must be 16-byte aligned");
+  if (((Wd * 3) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u)) return fail(VRGDG_E_ALIGN, "vrgdg_lanczos4_resize_u8: output must be 4-byte aligned");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  LanczosParams L;
+  L.B = B; L.Hs = Hs; L.Ws = Ws; L.Hd = Hd; L.Wd = Wd;
+  L.xofs = xofs; L.xcoef = xcoef; L.yofs = yofs; L.ycoef = ycoef;
+  cudaError_t e = launch_lanczos4(in, out, reinterpret_cast<int32_t*>(scratch), L, ctx);
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lanczos4_resize_u8");
   return VRGDG_OK;
 }
 

@@ -194,22 +194,39 @@ k_adjust_box(const float* __restrict__ src, float* __restrict__ dst_scratch, T* 
       }
       const int xq = x0 + (threadIdx.x & 15) * 4;
       const int64_t o = (((int64_t)frame * A.H + y) * A.W + xq) * 3;
-      if (!LAST && xq + 3 < A.W && (A.W & 3) == 0) {
-        float4* d4 = reinterpret_cast<float4*>(dst_scratch + o);
-        d4[0] = make_float4(res[0], res[1], res[2], res[3]);
-        d4[1] = make_float4(res[4], res[5], res[6], res[7]);
-        d4[2] = make_float4(res[8], res[9], res[10], res[11]);
-      } else {
+      // 4 whole pixels, and rows / base pointer aligned for the 4-element vector stores (16 B fp32, 8 B half, 4 B u8)
+      const bool whole = xq + 3 < A.W && (A.W & 3) == 0 &&
+                         (LAST ? (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(T) - 1)) == 0 : (reinterpret_cast<uintptr_t>(dst_scratch) & 15) == 0);
+      if (!LAST) {
+        if (whole) {
+          float4* d4 = reinterpret_cast<float4*>(dst_scratch + o);
+          d4[0] = make_float4(res[0], res[1], res[2], res[3]);
+          d4[1] = make_float4(res[4], res[5], res[6], res[7]);
+          d4[2] = make_float4(res[8], res[9], res[10], res[11]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const int px = j / 3, ch = j - px * 3;
-          if (xq + px >= A.W) continue;
-          if (LAST) {
-            const float m = vignette_mask(A, xq + px, y);
-            out[o + px * 3 + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res[j], m));
-          } else {
-            dst_scratch[o + j] = res[j];
+          for (int j = 0; j < 12; ++j)
+            if (xq + j / 3 < A.W) dst_scratch[o + j] = res[j];
+        }
+      } else {
+        union alignas(16) { T v[12]; uint4 q4[3]; uint2 q2[3]; uint32_t q1[3]; } pk;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float m = vignette_mask(A, min(xq + px, A.W - 1), y);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) pk.v[px * 3 + (BGR ? 2 - ch : ch)] = Elem<T>::st(adjust_stage_d(A, res[px * 3 + ch], m));
+        }
+        if (whole) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (sizeof(T) == 4) reinterpret_cast<uint4*>(out + o)[k] = pk.q4[k];
+            else if (sizeof(T) == 2) reinterpret_cast<uint2*>(out + o)[k] = pk.q2[k];
+            else reinterpret_cast<uint32_t*>(out + o)[k] = pk.q1[k];
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 12; ++j)
+            if (xq + j / 3 < A.W) out[o + j] = pk.v[j];
         }
       }
     }

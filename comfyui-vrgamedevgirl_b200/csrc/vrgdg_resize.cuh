@@ -9,7 +9,7 @@
 //   nearest : src = min(floor(dst * scale), in - 1)  (ATen "nearest", identity / exact-2x shortcuts give the same indices)
 //   bilinear: src = max(scale * (dst + 0.5) - 0.5, 0), two taps per axis
 //   bicubic : src = scale * (dst + 0.5) - 0.5, Keys kernel A = -0.75, four border-clamped taps per axis
-//   area    : adaptive average: rows floor(o*in/out) .. ceil((o+1)*in/out), summed in row-major order, divided by the count
+//   area    : adaptive average: rows floor(o*in/out) .. ceil((o+1)*in/out), summed in row-major order, then / rows / cols
 //
 // Nearest and area are bit-identical to torch; bilinear / bicubic agree to fp32 rounding (ATen picks between two differently
 // associated CPU kernels depending on the thread count, so "the" reference bit pattern is not defined; tests use 2e-6).
@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(256) k_resize(const T* __restrict__ in, T* __r
             for (int c = 0; c < 3; ++c) o[c] = addx(o[c], p[c]);
           }
         }
-        const float cnt = (float)((yb - ya) * (xb - xa));
+        const float kh = (float)(yb - ya), kw = (float)(xb - xa);    // ATen: scalar_t(sum / kh / kw), two roundings
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = divx(o[c], cnt);
+        for (int c = 0; c < 3; ++c) o[c] = divx(divx(o[c], kh), kw);
       }
     }
     T* dst = out + i * 3;

@@ -2,6 +2,7 @@
 caller's current stream.  Python allocates every output (torch's allocator owns frame memory)."""
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _native as nv
@@ -240,6 +241,52 @@ def blend(a, b, weight_a, weight_b):
     with torch.cuda.device(ta.device):
         nv.check(lib.vrgdg_blend(nv.ptr(ta), nv.ptr(tb), nv.ptr(out), ta.numel(), nv.DTYPE_CODE[ta.dtype], float(weight_a), float(weight_b),
                                  nv.stream_ptr(ta.device)))
+    return out
+
+
+_LANCZOS_TABLES = {}
+
+
+def lanczos4_tables(src_size, dst_size, device):
+    """(ofs int32 [dst], coef int16 [dst,8]) of one axis on `device`; built on the host by the library (OpenCV's recipe), cached."""
+    key = (int(src_size), int(dst_size), str(device))
+    hit = _LANCZOS_TABLES.get(key)
+    if hit is None:
+        ofs = np.empty(int(dst_size), dtype=np.int32)
+        coef = np.empty((int(dst_size), 8), dtype=np.int16)
+        lib = nv.load_library()
+        nv.check(lib.vrgdg_lanczos4_tables(int(src_size), int(dst_size), ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p)))
+        if len(_LANCZOS_TABLES) > 64:
+            _LANCZOS_TABLES.clear()
+        hit = _LANCZOS_TABLES[key] = (torch.from_numpy(ofs).to(device), torch.from_numpy(coef).to(device))
+    return hit
+
+
+def resize_lanczos4_u8(frames_u8, out_h, out_w, max_scratch_bytes=1 << 30):
+    """cv2.resize(INTER_LANCZOS4) of uint8 CUDA frames [B,H,W,3] -> [B,out_h,out_w,3], bit-identical to OpenCV
+    (vrgdg_lanczos4_resize_u8).  Frames are processed in groups so that the int32 scratch stays below max_scratch_bytes."""
+    if not isinstance(frames_u8, torch.Tensor) or frames_u8.device.type != "cuda" or frames_u8.dtype != torch.uint8 or frames_u8.ndim != 4 \
+            or frames_u8.shape[-1] != 3:
+        raise ValueError("vrgdg_b200: expected a CUDA uint8 tensor [B,H,W,3]")
+    s = frames_u8.contiguous()
+    B, H, W, _ = s.shape
+    oh, ow = max(1, int(out_h)), max(1, int(out_w))
+    out = torch.empty((B, oh, ow, 3), dtype=torch.uint8, device=s.device)
+    if B == 0:
+        return out
+    if H < 1 or W < 1:
+        raise ValueError("vrgdg_b200: cannot resize empty frames")
+    lib = nv.load_library()
+    xo, xc = lanczos4_tables(W, ow, s.device)
+    yo, yc = lanczos4_tables(H, oh, s.device)
+    per_frame = int(lib.vrgdg_lanczos4_scratch_bytes(1, H, ow))
+    group = max(1, min(B, max_scratch_bytes // max(1, per_frame)))
+    scratch = torch.empty((group * per_frame // 4,), dtype=torch.int32, device=s.device)
+    with torch.cuda.device(s.device):
+        for b0 in range(0, B, group):
+            n = min(group, B - b0)
+            nv.check(lib.vrgdg_lanczos4_resize_u8(nv.ptr(s[b0:b0 + n]), nv.ptr(out[b0:b0 + n]), n, H, W, oh, ow, nv.ptr(xo), nv.ptr(xc), nv.ptr(yo),
+                                                  nv.ptr(yc), nv.ptr(scratch), ctypes.c_int64(n * per_frame), nv.stream_ptr(s.device)))
     return out
 
 

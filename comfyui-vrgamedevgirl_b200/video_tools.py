@@ -103,6 +103,27 @@ def _auto_batch_size(width, height):
     return 1
 
 
+def _resize_frames(frames, output_width, output_height):
+    """EnhancerNodes.py:213-230: list of uint8 HWC frames -> list resized with cv2.INTER_LANCZOS4 semantics (bit-identical), frames
+    already at the output size are passed through untouched.  One upload / two launches / one download per group of equal-sized
+    frames; use ops.resize_lanczos4_u8 directly to stay on the device."""
+    output_width, output_height = max(1, int(output_width)), max(1, int(output_height))
+    resized = list(frames)
+    todo = {}
+    for i, frame in enumerate(frames):
+        if not (frame.shape[1] == output_width and frame.shape[0] == output_height):
+            todo.setdefault(tuple(frame.shape), []).append(i)
+    dev = compute_device()
+    for shape, idx in todo.items():
+        if len(shape) != 3 or shape[2] != 3 or frames[idx[0]].dtype != np.uint8:
+            raise ValueError("vrgdg_b200: _resize_frames expects uint8 [H,W,3] frames, got %s %s" % (shape, frames[idx[0]].dtype))
+        batch = torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in idx])).to(dev)
+        out = ops.resize_lanczos4_u8(batch, output_height, output_width).cpu().numpy()
+        for j, i in enumerate(idx):
+            resized[i] = out[j]
+    return resized
+
+
 def _apply_unsharp(images, strength, use_gpu):
     if strength <= 0:
         return images

@@ -231,6 +231,19 @@ VRGDG_API int vrgdg_resize(const void* in, void* out, int B, int Hs, int Ws, int
 VRGDG_API int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, float weight_a, float weight_b,
                 void* stream);
 
+/* ---- Lanczos4 resize of uint8 frames -----------------------------------------------------------------
+ * _resize_frames (VRGDG_StandaloneVideoEnhancerNodes.py:213-230) = cv2.resize(frame, (w, h), interpolation=cv2.INTER_LANCZOS4)
+ * on uint8 HWC frames; bit-identical to OpenCV 4.x (fixed-point 8-tap tables, border replication).
+ * vrgdg_lanczos4_tables is HOST code (no device work): for one axis it fills ofs[dst_size] (source index of the 4th tap) and
+ * coef[dst_size * 8] (weights x 2048 as shorts) exactly as OpenCV builds them; the caller uploads both axes' tables (coef
+ * 16-byte aligned) and passes device pointers.  scratch: vrgdg_lanczos4_scratch_bytes() of device memory, 16-byte aligned
+ * (the int32 horizontal pass).  in [B,Hs,Ws,3] u8 -> out [B,Hd,Wd,3] u8, channel order untouched. */
+VRGDG_API int vrgdg_lanczos4_tables(int src_size, int dst_size, int32_t* ofs, int16_t* coef);
+VRGDG_API int64_t vrgdg_lanczos4_scratch_bytes(int B, int Hs, int Wd);
+VRGDG_API int vrgdg_lanczos4_resize_u8(const uint8_t* in, uint8_t* out, int B, int Hs, int Ws, int Hd, int Wd,
+                             const int32_t* xofs, const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef,
+                             void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ---- uint8 BGR wire format -------------------------------------------------------------------------
  * _frames_to_tensor / _tensor_to_frames (VRGDG_LUTVideoTools.py:736-752,
  * VRGDG_StandaloneVideoEnhancerNodes.py:311-324): u8 BGR -> RGB float /255.0 and

@@ -68,7 +68,7 @@ def load_iv_adjustments():
 
 def load_enhancer_helpers():
     ns = {"torch": torch, "F": F}
-    names = {"_auto_batch_size", "_apply_unsharp", "_apply_seeded_grain", "_apply_effects_batch"}
+    names = {"_auto_batch_size", "_resize_frames", "_apply_unsharp", "_apply_seeded_grain", "_apply_effects_batch"}
     return _extract(os.path.join(REFERENCE_ROOT, "VRGDG_StandaloneVideoEnhancerNodes.py"), names, ns)
 
 

@@ -20,6 +20,8 @@ Parity status
 """
 import os
 
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -456,6 +458,72 @@ def restore_blend(originals, restored, strength):
     """VRGDG_VideoEnhanceNodes.py:408-414: lerp of the restored frames over the originals, clamp."""
     s = float(strength)
     return (originals * (1.0 - s) + restored * s).clamp(0, 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# the enhancer's Lanczos4 resize of uint8 frames (_resize_frames, VRGDG_StandaloneVideoEnhancerNodes.py:213-230)
+# The arithmetic lives in a dependency that is not vendored in the reference: OpenCV (cv2.resize, INTER_LANCZOS4; the pack pins
+# no version, this image has opencv 4.13.0).  Restated from OpenCV's published algorithm (imgproc/resize.cpp: interpolateLanczos4,
+# the 8-tap fixed-point tables with INTER_RESIZE_COEF_BITS = 11, HResizeLanczos4 / VResizeLanczos4 with border replication and
+# FixedPtCast<int, uchar, 22>) and pinned bit-exactly against cv2 itself (tests/golden/lanczos.npz, make_golden.py).
+# --------------------------------------------------------------------------------------------------
+def lanczos4_coeffs(x):
+    """interpolateLanczos4: 8 fp32 weights for the fractional offset x (an fp32 value)."""
+    s45 = 0.70710678118654752440084436210485
+    cs = ((1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45))
+    f32 = np.float32
+    y0 = float(-f32(f32(x) + f32(3))) * math.pi * 0.25           # (x+3) is a float sum in OpenCV; only then promoted to double
+    s0, c0 = math.sin(y0), math.cos(y0)
+    co, total = [], f32(0)
+    for i in range(8):
+        d = f32(f32(x) + f32(3) - f32(i))
+        if abs(d) >= f32(1e-6):
+            y = -float(d) * math.pi * 0.25
+            c = f32((cs[i][0] * s0 + cs[i][1] * c0) / (y * y))
+        else:
+            c = f32(1e30)
+        co.append(c)
+        total = f32(total + c)
+    inv = f32(f32(1) / total)
+    return [f32(c * inv) for c in co]
+
+
+def lanczos4_tables(ssize, dsize):
+    """per destination index: first-tap source index (sx, taps are sx-3 .. sx+4) and the 8 weights as saturated shorts (x 2048)."""
+    scale = 1.0 / (dsize / ssize)                                   # resize(): scale_x = 1. / inv_scale_x, doubles
+    ofs = np.zeros(dsize, np.int32)
+    coef = np.zeros((dsize, 8), np.int16)
+    for d in range(dsize):
+        fx = np.float32((d + 0.5) * scale - 0.5)
+        sx = math.floor(float(fx))
+        ofs[d] = sx
+        for k, c in enumerate(lanczos4_coeffs(np.float32(fx - np.float32(sx)))):
+            coef[d, k] = max(-32768, min(32767, int(np.rint(np.float32(c * np.float32(2048))))))   # saturate_cast<short>(cvRound)
+    return ofs, coef
+
+
+def resize_lanczos4_u8(frame, out_w, out_h):
+    """cv2.resize(frame, (out_w, out_h), interpolation=cv2.INTER_LANCZOS4) for a uint8 [H,W,C] frame."""
+    sh, sw = frame.shape[:2]
+    xo, xa = lanczos4_tables(sw, int(out_w))
+    yo, ya = lanczos4_tables(sh, int(out_h))
+    src = frame.astype(np.int32)
+    taps = np.arange(-3, 5)
+    xi = np.clip(xo[:, None] + taps[None, :], 0, sw - 1)
+    yi = np.clip(yo[:, None] + taps[None, :], 0, sh - 1)
+    h = np.zeros((sh, int(out_w), frame.shape[2]), np.int32)
+    for k in range(8):
+        h += src[:, xi[:, k], :] * xa[:, k].astype(np.int32)[None, :, None]
+    v = np.zeros((int(out_h), int(out_w), frame.shape[2]), np.int32)
+    for k in range(8):
+        v += h[yi[:, k]] * ya[:, k].astype(np.int32)[:, None, None]
+    return np.clip((v + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+
+
+def resize_frames(frames, output_width, output_height):
+    """_resize_frames, VRGDG_StandaloneVideoEnhancerNodes.py:213-230: frames already at the output size pass through."""
+    ow, oh = max(1, int(output_width)), max(1, int(output_height))
+    return [f if (f.shape[1] == ow and f.shape[0] == oh) else resize_lanczos4_u8(f, ow, oh) for f in frames]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -224,6 +224,27 @@ def main():
     save("resize", **rz)
     meta["resize_cases"] = RESIZE_CASES
 
+    # ---- the enhancer's Lanczos4 resize: cv2 itself is the reference (EnhancerNodes.py:213-230) ---------------------------------------
+    import cv2
+    se = RH.load_enhancer_helpers()
+    rngl = np.random.default_rng(77)
+    lz = {"cv2_version": np.array(cv2.__version__)}
+    LANCZOS_CASES = []
+    nat = (natural_frames(1, 90, 160, seed=86)[0].numpy()[..., ::-1] * 255).astype(np.uint8)
+    for name, img, (ow, oh) in (("noise_up", rngl.integers(0, 256, (37, 53, 3), dtype=np.uint8), (106, 74)),
+                                ("noise_down", rngl.integers(0, 256, (37, 53, 3), dtype=np.uint8), (31, 20)),
+                                ("noise_odd", rngl.integers(0, 256, (48, 64, 3), dtype=np.uint8), (100, 61)),
+                                ("tiny", rngl.integers(0, 256, (9, 7, 3), dtype=np.uint8), (3, 30)),
+                                ("float_sum_317", rngl.integers(0, 256, (64, 317, 3), dtype=np.uint8), (2252, 64)),   # x+3 rounded in fp32 matters here
+                                ("float_sum_500", rngl.integers(0, 256, (64, 500, 3), dtype=np.uint8), (378, 64)),
+                                ("extremes", (rngl.integers(0, 2, (40, 40, 3)) * 255).astype(np.uint8), (90, 70)),
+                                ("natural_up", nat, (320, 180)), ("natural_down", nat, (96, 54)), ("same", nat, (160, 90))):
+        lz[name + "_in"] = img
+        lz[name] = se["_resize_frames"]([img], ow, oh)[0]
+        LANCZOS_CASES.append([name, ow, oh])
+    save("lanczos", **lz)
+    meta["lanczos_cases"] = LANCZOS_CASES
+
     # ---- node API surface ---------------------------------------------------------------------------------------------
     api = {}
     classes = dict(nodes)

@@ -685,3 +685,50 @@ def test_restore_frames_blend_bit_exact(pkg, cuda_device, oracle):
     assert torch.equal(pkg.ops.blend(a, b, 1.0, 0.0), a.clamp(0, 1)) and torch.equal(pkg.ops.blend(a, b, 0.0, 1.0), b)
     with pytest.raises(ValueError):
         pkg.ops.blend(a, b[:2], 0.5, 0.5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the enhancer's cv2 Lanczos4 resize of uint8 frames: EnhancerNodes.py:213-230
+# ------------------------------------------------------------------------------------------------------
+def test_resize_frames_lanczos4_bit_exact_vs_cv2(pkg, cuda_device, meta):
+    import importlib
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    g = load_golden("lanczos")
+    for name, ow, oh in meta["lanczos_cases"]:
+        src = g[name + "_in"]
+        before = pkg._native.launch_count()
+        out = vt._resize_frames([src, src], ow, oh)
+        assert len(out) == 2 and out[0].dtype == np.uint8 and out[0].shape == g[name].shape, name
+        assert np.array_equal(out[0], g[name]) and np.array_equal(out[1], g[name]), name
+        if name == "same":
+            assert out[0] is src and pkg._native.launch_count() == before           # pass-through, like the reference (:221-222)
+        else:
+            assert pkg._native.launch_count() == before + 2, name                    # horizontal + vertical pass for the whole group
+    # mixed sizes in one call: each group of equal-sized frames is one batch
+    a, b = g["noise_up_in"], g["noise_odd_in"]
+    mixed = vt._resize_frames([a, b, a], 106, 74)
+    assert np.array_equal(mixed[0], g["noise_up"]) and np.array_equal(mixed[2], g["noise_up"]) and mixed[1].shape == (74, 106, 3)
+    with pytest.raises(ValueError):
+        vt._resize_frames([a.astype(np.float32)], 10, 10)
+    with pytest.raises(ValueError):
+        pkg.ops.resize_lanczos4_u8(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), 8, 8)     # CPU tensor: no CPU path
+
+
+def test_lanczos4_full_size_vs_oracle_and_properties(pkg, cuda_device, oracle):
+    """720p -> 1080p (the enhancer's upscale) against the oracle on a whole frame (~1 s CPU); plus size-independent properties at
+    4K: a constant frame stays constant (weights sum to 2048 only approximately -> within 1 code), frames are independent of the
+    batch they travel in, small scratch budgets (frame groups) give identical bytes."""
+    rng = np.random.default_rng(12)
+    f = torch.from_numpy(rng.integers(0, 256, (2, 720, 1280, 3), dtype=np.uint8)).to(cuda_device)
+    out = pkg.ops.resize_lanczos4_u8(f, 1080, 1920)
+    assert out.shape == (2, 1080, 1920, 3)
+    assert np.array_equal(out[1].cpu().numpy(), oracle.resize_lanczos4_u8(f[1].cpu().numpy(), 1920, 1080))
+    down = pkg.ops.resize_lanczos4_u8(out, 405, 721)                                       # odd sizes: scalar vertical pass (721*3 % 4 != 0)
+    assert np.array_equal(down[0].cpu().numpy(), oracle.resize_lanczos4_u8(out[0].cpu().numpy(), 721, 405))
+    big = torch.full((3, 1080, 1920, 3), 200, dtype=torch.uint8, device=cuda_device)
+    big[1] = torch.from_numpy(rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)).to(cuda_device)
+    up = pkg.ops.resize_lanczos4_u8(big, 2160, 3840)
+    assert int((up[0].int() - 200).abs().max()) <= 1 and torch.equal(up[0], up[2])
+    assert torch.equal(up[1], pkg.ops.resize_lanczos4_u8(big[1:2], 2160, 3840)[0])
+    assert torch.equal(up, pkg.ops.resize_lanczos4_u8(big, 2160, 3840, max_scratch_bytes=1))   # one frame per launch pair
+    assert pkg.ops.resize_lanczos4_u8(big[:0], 50, 60).shape == (0, 50, 60, 3)

@@ -202,3 +202,20 @@ def test_resize_plan_matches_the_reference_shapes(pkg, oracle):
     assert ve._interpolation("Area") == "area" and ve._interpolation("nope") == "bicubic"
     with pytest.raises(ValueError):
         ve._resize_batch(torch.zeros(0, 4, 4, 3), 8, 8, "Stretch to dimensions", "Nearest")
+
+
+def test_lanczos4_host_tables_match_the_oracle(pkg, oracle):
+    """vrgdg_lanczos4_tables is host code (no device work): OpenCV's 8-tap fixed-point tables, incl. the two size pairs where
+    rounding x + 3 in fp32 (as OpenCV does) rather than fp64 changes a weight (317 -> 2252 index 17, 500 -> 378 index 0)."""
+    import ctypes
+    lib = pkg._native.load_library()
+    for s_, d_ in ((317, 2252), (500, 378), (53, 106), (7, 3), (1, 5), (720, 1080), (1920, 1280), (64, 64), (1080, 2160)):
+        ofs, coef = np.empty(d_, np.int32), np.empty((d_, 8), np.int16)
+        assert lib.vrgdg_lanczos4_tables(s_, d_, ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p)) == 0
+        o2, c2 = oracle.lanczos4_tables(s_, d_)
+        assert np.array_equal(ofs, o2) and np.array_equal(coef, c2), (s_, d_)
+    ofs, coef = np.empty(64, np.int32), np.empty((64, 8), np.int16)
+    lib.vrgdg_lanczos4_tables(64, 64, ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(ofs, np.arange(64)) and np.array_equal(coef, np.tile(np.array([0, 0, 0, 2048, 0, 0, 0, 0], np.int16), (64, 1)))
+    assert lib.vrgdg_lanczos4_tables(0, 4, ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert lib.vrgdg_lanczos4_scratch_bytes(2, 10, 7) == 2 * 10 * 7 * 3 * 4

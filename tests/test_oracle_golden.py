@@ -123,6 +123,27 @@ def test_resize_restatement_bit_exact(oracle):
         oracle.resize_batch(t(g["x"])[0], 8, 8, "Stretch to dimensions", "Nearest")
 
 
+def test_lanczos4_restatement_bit_exact_vs_cv2_fixtures(oracle):
+    """_resize_frames (EnhancerNodes.py:213-230): the fixtures are outputs of cv2.resize itself (opencv version in the file)."""
+    g = load_golden("lanczos")
+    with open(os.path.join(GOLDEN, "reference_meta.json"), encoding="utf-8") as fh:
+        cases = json.load(fh)["lanczos_cases"]
+    assert {c[0] for c in cases} >= {"noise_up", "noise_down", "tiny", "float_sum_317", "float_sum_500", "extremes", "natural_up", "same"}
+    for name, ow, oh in cases:
+        src = g[name + "_in"]
+        out = oracle.resize_frames([src], ow, oh)[0]
+        assert np.array_equal(out, g[name]), name
+    assert oracle.resize_frames([g["same_in"]], 160, 90)[0] is g["same_in"]
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (45, 80, 3), dtype=np.uint8)
+    for ow, oh in ((120, 68), (33, 19), (80, 90)):
+        assert np.array_equal(oracle.resize_lanczos4_u8(img, ow, oh), cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LANCZOS4))
+
+
 def test_u8_restatement(oracle):
     g = load_golden("u8")
     assert torch.equal(oracle.frames_to_tensor(g["bgr"]), t(g["rgb_float"]))

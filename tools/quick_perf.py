@@ -117,6 +117,11 @@ def resize_lines():
         report(f"restore_blend/4x4k_{tag}", timeit(lambda: ops.blend(a, b, 0.35, 0.65)), 4 * 2160 * 3840, 9 * es)
         del small, big, a, b
         torch.cuda.empty_cache()
+    u = (natural_frames(8, 1080, 1920, seed=7, device=dev) * 255).to(torch.uint8)
+    report("lanczos4_u8_up2x/8x1080p", timeit(lambda: ops.resize_lanczos4_u8(u, 2160, 3840), iters=6, warm=2), 8 * 2160 * 3840, 3 * 1.25)
+    report("lanczos4_u8_up1.5x/8x720p", timeit(lambda: ops.resize_lanczos4_u8(u[:, :720, :1280].contiguous(), 1080, 1920), iters=6, warm=2), 8 * 1080 * 1920, 3 * (1 + 1 / 2.25))
+    u4 = (natural_frames(2, 2160, 3840, seed=8, device=dev) * 255).to(torch.uint8)
+    report("lanczos4_u8_down2x/2x4k", timeit(lambda: ops.resize_lanczos4_u8(u4, 1080, 1920), iters=6, warm=2), 2 * 1080 * 1920, 3 * 5)
 
 
 if __name__ == "__main__":
