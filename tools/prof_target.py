@@ -1,5 +1,5 @@
 """Runs one kernel family a few times so that ncu can capture it (GPU box only).
-    python tools/prof_target.py {chain|lut|grain|unsharp|colormatch} [f16|f32] [frames] [nat|white]"""
+    python tools/prof_target.py {chain|lut|grain|unsharp|colormatch|clarity|bicubic|lanczos} [f16|f32] [frames] [nat|white]"""
 import importlib
 import os
 import sys
@@ -32,6 +32,15 @@ elif what == "grain":
     fn = lambda: ops.grain(x, 0.04, 0.5, 0.5, seed=42)
 elif what == "unsharp":
     fn = lambda: ops.stencil3x3(x, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
+elif what == "clarity":
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    desc = vt._adjust_desc({"contrast": 10, "clarity": 50}, 1080, 1920)
+    fn = lambda: ops.adjust(x, desc)
+elif what == "bicubic":
+    fn = lambda: ops.resize(x[:4], 2160, 3840, "bicubic")
+elif what == "lanczos":
+    u = (x[:4].float() * 255).to(torch.uint8)
+    fn = lambda: ops.resize_lanczos4_u8(u, 2160, 3840)
 else:
     sums = ops.lab_moments(x)
     params = ops.colormatch_params(sums, sums[:1].contiguous())
