@@ -4,6 +4,7 @@
 
 The library lands in comfyui-vrgamedevgirl_b200/lib/ (git-ignored, travels to the GPU box with the snapshot).
 """
+import hashlib
 import os
 import shutil
 import subprocess
@@ -15,6 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libvrgdg_b200.so")
+STAMP = LIB + ".srchash"
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 UNITS = ["vrgdg_abi.cu", "vrgdg_f32.cu", "vrgdg_f16.cu", "vrgdg_bf16.cu", "vrgdg_u8.cu"]
 NVCC_FLAGS = [
@@ -31,16 +33,28 @@ def _nvcc():
 
 
 def _sources():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     out.append(os.path.join(INCLUDE, "vrgdg_b200.h"))
     return out
 
 
+def _source_hash():
+    """Content hash of every source the library is built from (mtimes do not survive a copy of the tree to another box)."""
+    h = hashlib.sha256()
+    for path in sorted(_sources()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS[:-1]).encode())
+    return h.hexdigest()
+
+
 def is_fresh():
-    if not os.path.exists(LIB):
+    """The library exists and was built from exactly the sources that are in the tree now."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(s) <= t for s in _sources())
+    with open(STAMP, encoding="utf-8") as fh:
+        return fh.read().strip() == _source_hash()
 
 
 def build(force=False, verbose=True):
@@ -68,6 +82,8 @@ def build(force=False, verbose=True):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    with open(STAMP, "w", encoding="utf-8") as fh:
+        fh.write(_source_hash() + "\n")
     if verbose:
         print("built", LIB)
     return LIB

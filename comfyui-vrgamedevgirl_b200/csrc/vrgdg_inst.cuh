@@ -87,7 +87,7 @@ static cudaError_t launch_tile_k(const CUtensorMap* tmap, const void* in, void* 
   cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (attr != cudaSuccess) return attr;
   constexpr int NT = TileCfg<T, MASK>::THREADS;
-  if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024)) + 1);
+  if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * TileCfg<T, MASK>::MINB * 100 / (228 * 1024)) + 1);
   static int occ = occupancy_of(kern, NT, smem);
   if (Q.total_tiles == 0) return cudaSuccess;
   const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx.sms * occ);

@@ -299,8 +299,11 @@ struct TileParams {
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
 };
 
-// HEAVY = the LUT gather runs in the pre-stage: one 512-thread CTA per SM with a 2-stage ring leaves ~126 KB of the
-// SM's 228 KB as L1 for the table; everything else uses 256-thread CTAs, a 3-stage ring and 2 CTAs per SM.
+// HEAVY = the LUT gather runs in the pre-stage.  Measured on the fused grain + LUT + unsharp chain (fp16 1080p, profiles/README.md):
+// one 480-thread CTA per SM 56.8 GPx/s, two 256-thread CTAs per SM 65.3-66.1 (while one CTA runs its stencil phase the other keeps
+// the L1 gather busy), three CTAs 58 (registers), 64-row tiles 65 but no room for a second CTA.  Two CTAs with a single staged
+// tile each (the stage is refilled while the stencil runs, see EARLY in k_tile) leave ~120 KB of the SM's 228 KB as L1 for the table.
+// Everything else uses 256-thread CTAs, a 3-stage ring and 2 CTAs per SM.
 // WORK = 16-bit frames with pre-stages: their fp32 results live in a separate work tile, and a thread then produces
 // 4 elements per row (16-byte shared loads at a 16-byte lane stride are bank-conflict free; 32-byte strides are not).
 template <typename T, int MASK> struct TileCfg {
@@ -312,19 +315,28 @@ template <typename T, int MASK> struct TileCfg {
   static constexpr int PADL = 16 / (int)sizeof(T);    // box starts 16 BYTES left of the tile: TMA needs a 16-byte aligned start address
   static constexpr int TXE = sizeof(T) == 1 ? 192 : 240;   // output elements per tile row: multiple of 6 and of VEC, TXE*sizeof(T) % 16 == 0 (every box start
                                                             // must be 16-byte aligned: an unaligned start is an illegal instruction), PADL + TXE + 3 <= BX
-  static constexpr int TY = 32;                       // output rows per tile
+#ifndef VRGDG_TILE_ROWS
+#define VRGDG_TILE_ROWS 32
+#endif
+  static constexpr int TY = VRGDG_TILE_ROWS;          // output rows per tile
   static constexpr int ROWS = TY + 2;
 #ifndef VRGDG_HEAVY_THREADS
-#define VRGDG_HEAVY_THREADS 480
+#define VRGDG_HEAVY_THREADS 256
 #endif
-  static constexpr int THREADS = HEAVY ? VRGDG_HEAVY_THREADS : 256;   // 34 x 42 = 1428 pair tasks = 2.975 rounds of 480 threads (512 would idle 7%)
-  static constexpr int MINB = HEAVY ? 1 : 2;
+  static constexpr int THREADS = HEAVY ? VRGDG_HEAVY_THREADS : 256;
+#ifndef VRGDG_HEAVY_MINB
+#define VRGDG_HEAVY_MINB 2
+#endif
+#ifndef VRGDG_HEAVY_NS
+#define VRGDG_HEAVY_NS (WORK ? 1 : 2)                 // in-place (fp32) tiles need the staged tile until the stencil is done
+#endif
+  static constexpr int MINB = HEAVY ? VRGDG_HEAVY_MINB : 2;
   static constexpr int COLS = TXE / VEC;              // threads across
   static constexpr int RG = (THREADS / COLS) >= 8 ? 8 : 4;   // row groups: COLS*RG active threads
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
-  static constexpr int NS = (HEAVY || GPLANE) ? 2 : 3;   // pipeline stages
+  static constexpr int NS = HEAVY ? VRGDG_HEAVY_NS : (GPLANE ? 2 : 3);   // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
   static_assert(TY % RG == 0 && COLS * RG <= THREADS, "thread mapping");
@@ -605,8 +617,17 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     tma_load_3d(reinterpret_cast<uint8_t*>(stage0) + (size_t)s * C::STAGE_BYTES, &tmap, x0e - PADL, y0 - 1, frame, &bars[s]);
   };
 
+  // WORK configurations copy the staged tile into the fp32 work tile in the pre-stage, so the stage is free again as soon as
+  // the pre-stage barrier has passed: its refill (tile k + NS) is issued there and overlaps the stencil phase; in-place
+  // configurations refill at the top of the next iteration (tile k + NS - 1 into the stage the previous iteration used).
+#ifndef VRGDG_EARLY_REFILL
+#define VRGDG_EARLY_REFILL 1
+#endif
+  constexpr bool EARLY = WORK && (VRGDG_EARLY_REFILL != 0);
+  constexpr uint32_t AHEAD = EARLY ? NS : NS - 1;
+  static_assert(AHEAD >= 1, "a single stage needs the early refill");
   if (tma && tid == 0) {
-    for (uint32_t k = 0; k < NS - 1 && k < n_my; ++k) issue(k);
+    for (uint32_t k = 0; k < AHEAD && k < n_my; ++k) issue(k);
   }
 
   for (uint32_t k = 0; k < n_my; ++k) {
@@ -616,7 +637,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     T* raw = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(stage0) + (size_t)s * C::STAGE_BYTES);
 
     if (tma) {
-      if (tid == 0 && k + NS - 1 < n_my) {
+      if (!EARLY && tid == 0 && k + NS - 1 < n_my) {
         fence_proxy_async();          // order earlier generic-proxy accesses of that stage before the async write
         issue(k + NS - 1);
       }
@@ -699,6 +720,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
         }
       }
       __syncthreads();
+      if (EARLY && tma && tid == 0 && k + NS < n_my) {
+        fence_proxy_async();          // the pre-stage's generic-proxy reads of this stage happen-before the async refill
+        issue(k + NS);
+      }
     }
 
     if (Q.border == 0) {
