@@ -21,7 +21,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 UNITS = ["vrgdg_abi.cu", "vrgdg_f32.cu", "vrgdg_f16.cu", "vrgdg_bf16.cu", "vrgdg_u8.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE,
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xfatbin", "-compress-all", "-I", INCLUDE,
 ]
 
 

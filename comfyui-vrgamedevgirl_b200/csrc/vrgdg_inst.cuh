@@ -51,7 +51,9 @@ cudaError_t launch_point(const void* in, void* out, const PointParams& P, int ma
   // masks without grain have no inexact variant (colour match always rounds like the reference; LUT alone is exact)
 #define VRGDG_PT(M)                                                                    \
   case M:                                                                              \
-    if (((M) & ST_GRAIN) && !exact) return launch_point_v<T, M, false>(in, out, P, ctx); \
+    if constexpr (((M) & ST_GRAIN) != 0) {                                             \
+      if (!exact) return launch_point_v<T, M, false>(in, out, P, ctx);                 \
+    }                                                                                  \
     return launch_point_v<T, M, true>(in, out, P, ctx);
   switch (mask) {
     VRGDG_PT(1) VRGDG_PT(2) VRGDG_PT(3) VRGDG_PT(4) VRGDG_PT(5) VRGDG_PT(6) VRGDG_PT(7)
@@ -103,7 +105,9 @@ cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, Tile
                         const LaunchCtx& ctx) {
 #define VRGDG_TL(M)                                                                        \
   case M:                                                                                  \
-    if (((M) & ST_GRAIN) && !exact) return launch_tile_k<T, M, false>(tmap, in, out, Q, ctx); \
+    if constexpr (((M) & ST_GRAIN) != 0) {                                                 \
+      if (!exact) return launch_tile_k<T, M, false>(tmap, in, out, Q, ctx);                \
+    }                                                                                      \
     return launch_tile_k<T, M, true>(tmap, in, out, Q, ctx);
   switch (mask) {
     VRGDG_TL(0) VRGDG_TL(1) VRGDG_TL(2) VRGDG_TL(3) VRGDG_TL(4) VRGDG_TL(5) VRGDG_TL(6) VRGDG_TL(7)

@@ -377,26 +377,35 @@ __device__ __forceinline__ void fix_border(E* tile, int y0, int x0e, int H, int 
   __syncthreads();
 }
 
+// 128-bit shared load that the compiler cannot narrow: when only 3 of the 4 words are used it turns a plain float4 load into
+// LDS.32 + LDS.64, and those run into 4-way bank conflicts at the 16-byte lane stride of the stencil (ncu: 35 % of the fused
+// chain's shared wavefronts were excess).  Whole 16-byte accesses at a 16-byte lane stride are conflict free.
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
 // window row: WN = VEC+6 floats starting at element (f0 - 3) of the tile row
 template <typename E, int VEC>
 __device__ __forceinline__ void load_window(const E* rowp /* -> tile column PADL+f0 */, float* w) {
   if (sizeof(E) == 4) {
-    // floats [f0-4, f0+VEC+4): (VEC+8)/4 aligned float4
+    // floats [f0-4, f0+VEC+4): (VEC+8)/4 aligned 16-byte words
     constexpr int NV = (VEC + 8) / 4;
     float tmp[NV * 4];
-    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) - 4);
+    const float* p = reinterpret_cast<const float*>(rowp) - 4;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float4 q = p[i];
-      tmp[4 * i] = q.x; tmp[4 * i + 1] = q.y; tmp[4 * i + 2] = q.z; tmp[4 * i + 3] = q.w;
+      const uint4 q = lds128(p + 4 * i);
+      tmp[4 * i] = __uint_as_float(q.x); tmp[4 * i + 1] = __uint_as_float(q.y);
+      tmp[4 * i + 2] = __uint_as_float(q.z); tmp[4 * i + 3] = __uint_as_float(q.w);
     }
 #pragma unroll
     for (int i = 0; i < VEC + 6; ++i) w[i] = tmp[i + 1];
   } else {
-    // 16-bit elements [f0-8, f0+16): three aligned uint4 (VEC == 8)
+    // 16-bit elements [f0-8, f0+16): three aligned 16-byte words (VEC == 8)
     union { uint4 q[3]; E e[24]; } u;
-    const uint4* p = reinterpret_cast<const uint4*>(rowp - 8);
-    u.q[0] = p[0]; u.q[1] = p[1]; u.q[2] = p[2];
+    u.q[0] = lds128(rowp - 8); u.q[1] = lds128(rowp); u.q[2] = lds128(rowp + 8);
 #pragma unroll
     for (int i = 0; i < VEC + 6; ++i) w[i] = Elem<E>::ld(u.e[i + 5]);
   }
@@ -503,7 +512,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, co
           o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
           o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
         }
-      } else if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
+      } else if ((MASK & 7) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
     }
   } else {
@@ -529,7 +538,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, co
           o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
           o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
         }
-      } else if (Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);
+      } else if ((MASK & 7) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
 #pragma unroll
       for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
