@@ -201,12 +201,12 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 
 // ---- 3D LUT trilinear: VRGDG_IV_Adjustments.py:293-336 ------------------------------------------
 // Device table layout ("cell table", built by lut_pack_entry / vrgdg_lut3d_pack): one 96-byte entry per cell origin
-//   entry (b,g,r) = { c000 c100 c010 c110 c001 c101 c011 c111 } x rgb,  cXYZ = lut[min(b+Z,S-1), min(g+Y,S-1), min(r+X,S-1), :]
-// so a pixel fetches its 8 corners (24 floats) with THREE 256-bit loads (LDG.E.256) from consecutive addresses instead of
-// 24 scalar loads.  The gather is bound by L1 tag lookups per divergent lane, not by bytes (profiles/: 4 lookups/px with a
+//   entry (b,g,r) = rgb x { c000 c100 c010 c110 c001 c101 c011 c111 },  cXYZ = lut[min(b+Z,S-1), min(g+Y,S-1), min(r+X,S-1), :]
+// (channel-planar: one 32-byte sector per output channel) so a pixel fetches its 8 corners (24 floats) with THREE 256-bit
+// loads (LDG.E.256) from consecutive addresses instead of 24 scalar loads - or three lanes fetch one sector each.  The gather is bound by L1 tag lookups per divergent lane, not by bytes (profiles/: 4 lookups/px with a
 // 32-byte r-pair table = 60-65 Gpx/s on grained frames, 3 lookups/px with this layout = 73-84 Gpx/s, 24 scalar = 34).
 struct LutParams {
-  const float* lut;      // cell table, S*S*S*24 floats
+  const float* lut;      // cell table, S*S*S*24 floats: per cell three 32-byte sectors (R, G, B), 8 corners each
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -239,7 +239,7 @@ VRGDG_HD void lut_pack_entry(const float* lut3, int S, int b, int g, int r, floa
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float* a = lut3 + ((size_t)(cb[k] * S + cg[k]) * S + cr[k]) * 3;
-    dst24[3 * k] = a[0]; dst24[3 * k + 1] = a[1]; dst24[3 * k + 2] = a[2];
+    dst24[k] = a[0]; dst24[8 + k] = a[1]; dst24[16 + k] = a[2];     // channel-planar: one 32-byte sector per output channel
   }
 }
 
@@ -260,6 +260,18 @@ VRGDG_HD float lerp_ref(float a, float b, float f, float omf) {
   return fmaf(f, b - a, a);                           // contracted form for fused chains (<= 2e-7 away)
 }
 
+// one channel from its sector q = {c000 c100 c010 c110 c001 c101 c011 c111} (cXYZ: X = r, Y = g, Z = b neighbour), :318-339
+template <bool EXACT>
+VRGDG_HD float lut_channel(const F8& q, float fr, float fg, float fb, float omr, float omg, float omb) {
+  const float c00 = lerp_ref<EXACT>(q.v[0], q.v[4], fb, omb);     // c000*(1-fb) + c001*fb
+  const float c01 = lerp_ref<EXACT>(q.v[2], q.v[6], fb, omb);     // c010, c011
+  const float c10 = lerp_ref<EXACT>(q.v[1], q.v[5], fb, omb);     // c100, c101
+  const float c11 = lerp_ref<EXACT>(q.v[3], q.v[7], fb, omb);     // c110, c111
+  const float c0 = lerp_ref<EXACT>(c00, c01, fg, omg);
+  const float c1 = lerp_ref<EXACT>(c10, c11, fg, omg);
+  return clamp01(lerp_ref<EXACT>(c0, c1, fr, omr));
+}
+
 template <bool EXACT>
 VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   int r0, r1, g0, g1, b0, b1;
@@ -270,23 +282,25 @@ VRGDG_HD void lut3d_eval(const LutParams& P, float& r, float& g, float& b) {
   (void)r1; (void)g1; (void)b1;                     // the clamped neighbours are baked into the cell entry
   const float* p = P.lut + (size_t)((b0 * P.S + g0) * P.S + r0) * LUT_CELL_FLOATS;
   const F8 q0 = lut_load8(p), q1 = lut_load8(p + 8), q2 = lut_load8(p + 16);
-  // v[3k+ch]: k = 0..7 -> c000 c100 c010 c110 c001 c101 c011 c111
-  const float v[24] = {q0.v[0], q0.v[1], q0.v[2], q0.v[3], q0.v[4], q0.v[5], q0.v[6], q0.v[7],
-                       q1.v[0], q1.v[1], q1.v[2], q1.v[3], q1.v[4], q1.v[5], q1.v[6], q1.v[7],
-                       q2.v[0], q2.v[1], q2.v[2], q2.v[3], q2.v[4], q2.v[5], q2.v[6], q2.v[7]};
   const float omb = subx(1.0f, fb), omg = subx(1.0f, fg), omr = subx(1.0f, fr);
-  float o[3];
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    float c00 = lerp_ref<EXACT>(v[0 + ch], v[12 + ch], fb, omb);     // c000*(1-fb) + c001*fb
-    float c01 = lerp_ref<EXACT>(v[6 + ch], v[18 + ch], fb, omb);     // c010, c011
-    float c10 = lerp_ref<EXACT>(v[3 + ch], v[15 + ch], fb, omb);     // c100, c101
-    float c11 = lerp_ref<EXACT>(v[9 + ch], v[21 + ch], fb, omb);     // c110, c111
-    float c0 = lerp_ref<EXACT>(c00, c01, fg, omg);
-    float c1 = lerp_ref<EXACT>(c10, c11, fg, omg);
-    o[ch] = clamp01(lerp_ref<EXACT>(c0, c1, fr, omr));
-  }
-  r = o[0]; g = o[1]; b = o[2];
+  r = lut_channel<EXACT>(q0, fr, fg, fb, omr, omg, omb);
+  g = lut_channel<EXACT>(q1, fr, fg, fb, omr, omg, omb);
+  b = lut_channel<EXACT>(q2, fr, fg, fb, omr, omg, omb);
+}
+
+// One output channel only: the element-mapped gather of the tile kernels (three lanes of a pixel read the three sectors of
+// one cell, i.e. one or two 128-byte lines per PIXEL instead of three per pixel: the L1 data pipe counts wavefronts per
+// distinct line and instruction; measured 73 -> 108 Gpx/s on grained frames, tools/lut_bench.cu v10 vs v13).
+template <bool EXACT>
+VRGDG_HD float lut3d_eval_channel(const LutParams& P, float r, float g, float b, int ch) {
+  int r0, r1, g0, g1, b0, b1;
+  float fr, fg, fb;
+  lut_coord(r, P.dmin[0], P.dspan[0], P.unit_domain != 0, P.smax, P.S, r0, r1, fr);
+  lut_coord(g, P.dmin[1], P.dspan[1], P.unit_domain != 0, P.smax, P.S, g0, g1, fg);
+  lut_coord(b, P.dmin[2], P.dspan[2], P.unit_domain != 0, P.smax, P.S, b0, b1, fb);
+  (void)r1; (void)g1; (void)b1;
+  const F8 q = lut_load8(P.lut + (size_t)((b0 * P.S + g0) * P.S + r0) * LUT_CELL_FLOATS + 8 * ch);
+  return lut_channel<EXACT>(q, fr, fg, fb, subx(1.0f, fr), subx(1.0f, fg), subx(1.0f, fb));
 }
 
 // Two pixels at once: both address computations first, then all six 256-bit loads, then the lerps, so that the two
@@ -306,22 +320,10 @@ VRGDG_HD LutCell lut_locate(const LutParams& P, float r, float g, float b) {
 
 template <bool EXACT>
 VRGDG_HD void lut_finish(const LutCell& c, const F8& q0, const F8& q1, const F8& q2, float& r, float& g, float& b) {
-  const float v[24] = {q0.v[0], q0.v[1], q0.v[2], q0.v[3], q0.v[4], q0.v[5], q0.v[6], q0.v[7],
-                       q1.v[0], q1.v[1], q1.v[2], q1.v[3], q1.v[4], q1.v[5], q1.v[6], q1.v[7],
-                       q2.v[0], q2.v[1], q2.v[2], q2.v[3], q2.v[4], q2.v[5], q2.v[6], q2.v[7]};
   const float omb = subx(1.0f, c.fb), omg = subx(1.0f, c.fg), omr = subx(1.0f, c.fr);
-  float o[3];
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    float c00 = lerp_ref<EXACT>(v[0 + ch], v[12 + ch], c.fb, omb);
-    float c01 = lerp_ref<EXACT>(v[6 + ch], v[18 + ch], c.fb, omb);
-    float c10 = lerp_ref<EXACT>(v[3 + ch], v[15 + ch], c.fb, omb);
-    float c11 = lerp_ref<EXACT>(v[9 + ch], v[21 + ch], c.fb, omb);
-    float c0 = lerp_ref<EXACT>(c00, c01, c.fg, omg);
-    float c1 = lerp_ref<EXACT>(c10, c11, c.fg, omg);
-    o[ch] = clamp01(lerp_ref<EXACT>(c0, c1, c.fr, omr));
-  }
-  r = o[0]; g = o[1]; b = o[2];
+  r = lut_channel<EXACT>(q0, c.fr, c.fg, c.fb, omr, omg, omb);
+  g = lut_channel<EXACT>(q1, c.fr, c.fg, c.fb, omr, omg, omb);
+  b = lut_channel<EXACT>(q2, c.fr, c.fg, c.fb, omr, omg, omb);
 }
 
 template <bool EXACT>

@@ -66,6 +66,9 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
       float a[3] = {r, g, b}, c[3] = {r, g, b};
       lut3d_eval2<true>(P, a, c);
       r = c[0]; g = a[1]; b = c[2];
+    } else if (exact == 3) {                                         // the element-mapped form of the tile kernels (one channel per call)
+      const float o0 = lut3d_eval_channel<true>(P, r, g, b, 0), o1 = lut3d_eval_channel<true>(P, r, g, b, 1), o2 = lut3d_eval_channel<true>(P, r, g, b, 2);
+      r = o0; g = o1; b = o2;
     } else lut3d_eval<false>(P, r, g, b);
     if (blend < 1.0f) {
       if (exact) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }

@@ -101,6 +101,8 @@ def test_lut_eval_exact_is_bit_identical(hostcheck, oracle):
         assert np.abs(o - flat(g[f"{key}__s10"])).max() < 1e-6
         hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 2)      # two-pixel form
         assert np.array_equal(o, flat(g[f"{key}__s10"])), fname
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), blend, 1.0 - blend, 3)   # one channel per lane (tile kernels)
+        assert np.array_equal(o, flat(g[f"{key}__s3p5"])), fname
 
 
 def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):

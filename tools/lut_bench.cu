@@ -181,6 +181,53 @@ __global__ void __launch_bounds__(256) k_lut(const T* __restrict__ in, T* __rest
   }
 }
 
+// ---- variant 12/13: one thread per ELEMENT (pixel, channel); channel-planar cell = 3 sectors of 8 corners; the three lanes of a
+// pixel read three sectors of the same cell -> one 128-byte line (STRIDE 32, padded) or at most two (STRIDE 24) per pixel ------------
+template <typename T, int STRIDE>
+__global__ void __launch_bounds__(256) k_lut_elem(const T* __restrict__ in, T* __restrict__ out, int64_t npix, const float* __restrict__ lute, int S) {
+  const int64_t nel = npix * 3;
+  const float smax = (float)(S - 1);
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < nel; e += (int64_t)gridDim.x * 256) {
+    const int64_t px = e / 3;
+    const int ch = (int)(e - px * 3);
+    const T* s = in + px * 3;
+    float r = E<T>::ld(__ldg(s)), g = E<T>::ld(__ldg(s + 1)), b = E<T>::ld(__ldg(s + 2));
+    Idx q;
+    coord<false>(r, smax, S, q.r0, q.r1, q.fr); coord<false>(g, smax, S, q.g0, q.g1, q.fg); coord<false>(b, smax, S, q.b0, q.b1, q.fb);
+    const float* p = lute + (size_t)((q.b0 * S + q.g0) * S + q.r0) * STRIDE + ch * 8;
+    F8 a = ld256(p);   // c000 c100 c010 c110 c001 c101 c011 c111 of this channel
+    float omb = 1.f - q.fb, omg = 1.f - q.fg, omr = 1.f - q.fr;
+    float c00 = lerp1<true>(a.a.x, a.b.x, q.fb, omb), c10 = lerp1<true>(a.a.y, a.b.y, q.fb, omb);
+    float c01 = lerp1<true>(a.a.z, a.b.z, q.fb, omb), c11 = lerp1<true>(a.a.w, a.b.w, q.fb, omb);
+    out[e] = E<T>::st(clamp01(lerp1<true>(lerp1<true>(c00, c01, q.fg, omg), lerp1<true>(c10, c11, q.fg, omg), q.fr, omr)));
+  }
+}
+
+template <typename T, int STRIDE>
+void run_elem(const char* name, const char* tname, const T* in, T* out, int64_t npix, const float* le, int S, int sms, const char* dist, const T* check) {
+  auto kern = k_lut_elem<T, STRIDE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+  int grid = sms * (occ > 0 ? occ : 1) * 4;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int i = 0; i < 2; ++i) kern<<<grid, 256>>>(in, out, npix, le, S);
+  CK(cudaDeviceSynchronize());
+  float best = 1e9f;
+  for (int i = 0; i < 5; ++i) {
+    CK(cudaEventRecord(a)); kern<<<grid, 256>>>(in, out, npix, le, S); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); best = fminf(best, ms);
+  }
+  size_t n = 3 << 18;
+  std::vector<T> h1(n), h2(n);
+  CK(cudaMemcpy(h1.data(), out, n * sizeof(T), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2.data(), check, n * sizeof(T), cudaMemcpyDeviceToHost));
+  double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs((double)(float)h1[i] - (double)(float)h2[i]));
+  double gpx = npix / (best * 1e-3) / 1e9;
+  printf("{\"variant\": \"%s\", \"dtype\": \"%s\", \"dist\": \"%s\", \"S\": %d, \"ms\": %.4f, \"Gpx/s\": %.1f, \"GB/s\": %.0f, \"occ\": %d, \"maxdiff_vs_v1\": %.3g}\n",
+         name, tname, dist, S, best, gpx, gpx * 6 * sizeof(T), occ, md);
+  fflush(stdout);
+}
+
 template <typename T> __global__ void k_fill(T* p, int64_t npix, int W, int H, int mode, uint32_t seed) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < npix; i += (int64_t)gridDim.x * 256) {
     int x = (int)(i % W), y = (int)((i / W) % H);
@@ -267,6 +314,14 @@ template <typename T> void suite(const char* tname, int sms) {
       hq[i * 16 + 2 * k] = q[0] | (q[1] << 21);
       hq[i * 16 + 2 * k + 1] = (q[1] >> 11) | (q[2] << 10);
     }
+    std::vector<float> he32(n * 32, 0.f), he24(n * 24, 0.f);
+    for (size_t i = 0; i < n; ++i) for (int k = 0; k < 8; ++k) for (int c = 0; c < 3; ++c) {
+      he32[i * 32 + c * 8 + k] = hc[i * 24 + k * 3 + c];
+      he24[i * 24 + c * 8 + k] = hc[i * 24 + k * 3 + c];
+    }
+    float *le32, *le24;
+    CK(cudaMalloc(&le32, n * 128)); CK(cudaMemcpy(le32, he32.data(), n * 128, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&le24, n * 96)); CK(cudaMemcpy(le24, he24.data(), n * 96, cudaMemcpyHostToDevice));
     float* lq; CK(cudaMalloc(&lq, n * 64)); CK(cudaMemcpy(lq, hq.data(), n * 64, cudaMemcpyHostToDevice));
     float *l3, *lp, *lc; float4* l4;
     CK(cudaMalloc(&l3, n * 12)); CK(cudaMalloc(&l4, n * 16)); CK(cudaMalloc(&lp, n * 32)); CK(cudaMalloc(&lc, n * 96));
@@ -287,10 +342,12 @@ template <typename T> void suite(const char* tname, int sms) {
       run<T, 6>("v6_pair_256_fast", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref);
       run<T, 10>("v10_cell_3x256_exact", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc);
       run<T, 11>("v11_cell_u21_2x256", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc, lq);
+      run_elem<T, 32>("v12_elem_planar_pad128", tname, in, out, npix, le32, S, sms, dist, ref);
+      run_elem<T, 24>("v13_elem_planar_96", tname, in, out, npix, le24, S, sms, dist, ref);
       if (n * 12 <= 200 * 1024) run<T, 7>("v7_smem_scalar_exact", tname, in, out, npix, l3, l4, lp, S, n * 12, sms, dist, ref);
       if (n * 16 <= 200 * 1024) run<T, 8>("v8_smem_f4_exact", tname, in, out, npix, l3, l4, lp, S, n * 16, sms, dist, ref);
     }
-    cudaFree(l3); cudaFree(l4); cudaFree(lp); cudaFree(lc); cudaFree(lq);
+    cudaFree(l3); cudaFree(l4); cudaFree(lp); cudaFree(lc); cudaFree(lq); cudaFree(le32); cudaFree(le24);
   }
   cudaFree(in); cudaFree(out); cudaFree(ref);
 }
