@@ -25,9 +25,20 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-if "reference" in sys.argv:      # the CPU arm uses every host thread; torchrun would otherwise pin OMP_NUM_THREADS=1
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+def host_threads():
+    """Threads for the CPU arm: one per PHYSICAL core (torch's own default; measured on the GPU box: 128 SMT threads run the
+    reference chain 3x slower than 64)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        n = None
+    return int(n or max(1, (os.cpu_count() or 2) // 2))
+
+
+if "reference" in sys.argv:      # the CPU arm uses every core; torchrun would otherwise pin OMP_NUM_THREADS=1
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
+    os.environ["MKL_NUM_THREADS"] = str(host_threads())
 
 import torch  # noqa: E402
 
@@ -129,7 +140,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     torch.set_num_threads(threads)
     sample_frames = 4
     import vrgdg_oracle as oracle
