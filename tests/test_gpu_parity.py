@@ -732,3 +732,51 @@ def test_lanczos4_full_size_vs_oracle_and_properties(pkg, cuda_device, oracle):
     assert torch.equal(up[1], pkg.ops.resize_lanczos4_u8(big[1:2], 2160, 3840)[0])
     assert torch.equal(up, pkg.ops.resize_lanczos4_u8(big, 2160, 3840, max_scratch_bytes=1))   # one frame per launch pair
     assert pkg.ops.resize_lanczos4_u8(big[:0], 50, 60).shape == (0, 50, 60, 3)
+
+
+# ------------------------------------------------------------------------------------------------------
+# ragged shapes: every loader / border / tail path against the oracle (small frames: the oracle needs milliseconds)
+# ------------------------------------------------------------------------------------------------------
+def test_random_ragged_shapes_bit_exact_vs_oracle(pkg, cuda_device, oracle):
+    """40 random shapes (1 x 1 up to 3 x 75 x 530: below / above the 34-row and 256-element TMA limits, widths that are not a
+    multiple of 4, single rows and columns): the exact-arithmetic kernels must equal the oracle bit for bit on all of them, the
+    TMA and the bounds-checked loaders must agree, and the uint8 path must equal codecs around the float path."""
+    nv = pkg._native
+    rng = np.random.default_rng(2024)
+    lut = _lut33(pkg)
+    olut = oracle.parse_cube(os.path.join(LUTS, "B200 Vintage 33.cube"))
+    shapes = [(1, 1, 1), (1, 1, 7), (2, 9, 1), (1, 2, 2), (1, 34, 86), (1, 35, 88), (1, 33, 340), (2, 70, 84), (1, 36, 529)]
+    while len(shapes) < 40:
+        shapes.append((int(rng.integers(1, 4)), int(rng.integers(1, 76)), int(rng.integers(1, 531))))
+    seen_tma = False
+    for i, (B, H, W) in enumerate(shapes):
+        x = torch.from_numpy(rng.random((B, H, W, 3), dtype=np.float32) * 1.2 - 0.1)
+        z = torch.from_numpy(rng.standard_normal((B, H, W, 3)).astype(np.float32))
+        xd, zd = x.to(cuda_device), z.to(cuda_device)
+        tag = (B, H, W)
+        # stencils, NumPy-path semantics (edge-replicated border)
+        for op, fn in ((nv.STENCIL_BOX_UNSHARP, oracle.unsharp_numpy), (nv.STENCIL_LAPLACIAN_CPU, oracle.laplacian_numpy),
+                       (nv.STENCIL_SOBEL_CPU, oracle.sobel_numpy))[i % 3:i % 3 + 1]:
+            got = pkg.ops.stencil3x3(xd, op, 0.7, nv.BORDER_REPLICATE)
+            seen_tma |= nv.last_tile_path() == "tma"
+            assert torch.equal(got.cpu(), fn(x, 0.7)), (tag, op)
+            os.environ["VRGDG_NO_TMA"] = "1"
+            try:
+                assert torch.equal(pkg.ops.stencil3x3(xd, op, 0.7, nv.BORDER_REPLICATE), got), (tag, op, "generic loader")
+            finally:
+                del os.environ["VRGDG_NO_TMA"]
+        # LUT node arithmetic, strength blend
+        lut_dev = pkg.ops.pack_lut(lut["lut"], cuda_device)
+        got = pkg.ops.lut3d_apply(xd, lut_dev, [0, 0, 0], [1, 1, 1], 0.35, 1.0 - 0.35)
+        assert torch.equal(got.cpu(), oracle.apply_lut(x, olut, 3.5)), tag
+        # fused chain on the reference's noise
+        chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), lut=dict(lut_data=lut, strength=10.0),
+                                    stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5, border=nv.BORDER_REPLICATE), device=cuda_device)
+        got = chain(xd, ext_noise=zd)
+        assert torch.equal(got.cpu(), oracle.chain_grain_lut_unsharp(x, z, 0.04, 0.5, olut, 10.0, 0.5)), tag
+        # uint8 BGR frames through the same chain == decode -> float chain -> encode
+        u8 = torch.from_numpy(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)).to(cuda_device)
+        a = chain(u8, ext_noise=zd)
+        b = pkg.ops.rgb_to_u8bgr(chain(pkg.ops.u8bgr_to_rgb(u8), ext_noise=zd))
+        assert a.dtype == torch.uint8 and torch.equal(a, b), tag
+    assert seen_tma                                                             # the list covers both loaders
