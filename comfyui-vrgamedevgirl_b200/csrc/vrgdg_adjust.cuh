@@ -53,8 +53,8 @@ __device__ __forceinline__ void adjust_stage_a(const AdjustParams& A, float& r, 
   const float l2 = adj_luma(v[0], v[1], v[2]);
   const float hm = clamp01(divx(subx(l2, 0.55f), 0.45f));
   const float sm = clamp01(divx(subx(0.45f, l2), 0.45f));
-  const float wm = clamp01(divx(subx(l2, 0.75f), 0.25f));
-  const float bm = clamp01(divx(subx(0.25f, l2), 0.25f));
+  const float wm = clamp01(mulx(subx(l2, 0.75f), 4.0f));        // / 0.25: a power of two, the product is the exact quotient
+  const float bm = clamp01(mulx(subx(0.25f, l2), 4.0f));
   const float t1 = mulx(hm, A.hl), t2 = mulx(sm, A.sh), t3 = mulx(wm, A.wh), t4 = mulx(bm, A.bl);
 #pragma unroll
   for (int c = 0; c < 3; ++c) v[c] = addx(addx(addx(addx(v[c], t1), t2), t3), t4);
@@ -178,13 +178,13 @@ k_adjust_box(const float* __restrict__ src, float* __restrict__ dst_scratch, T* 
       for (int j = 0; j < 12; ++j) {
         const float xc = ctr[j];
         res[j] = xc;
-        if (K >= 3) {
-          const float blur = divx(acc[j], (float)(K * K));              // avg_pool2d: sum / (K*K)
+        if constexpr (K >= 3) {
+          const float blur = div_const<K * K>(acc[j]);                  // avg_pool2d: sum / (K*K), correctly rounded (div_const)
           const float detail = subx(xc, blur);
           if (MODE == 0) {
             const int p = (j / 3) * 3;                                   // this pixel's r, g, b
             const float ln = adj_luma(ctr[p], ctr[p + 1], ctr[p + 2]);
-            const float mid = subx(1.0f, clamp01(divx(fabsf(subx(ln, 0.5f)), 0.5f)));
+            const float mid = subx(1.0f, clamp01(mulx(fabsf(subx(ln, 0.5f)), 2.0f))   /* / 0.5 */);
             const float wgt = addx(0.35f, mulx(mid, 0.65f));
             res[j] = addx(xc, mulx(mulx(mulx(detail, A.clarity), 1.55f), wgt));   // nchw + detail * clarity * 1.55 * (0.35 + mid*0.65)
           } else {

@@ -38,6 +38,23 @@ VRGDG_HD float sqrtx(float a) { return sqrtf(a); }
 
 VRGDG_HD float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
+// a / D for the integer constants the exact kernels divide by (9, 25, 49, 81, 255): q = a*r, q' = fma(fma(-D, q, a), r, q) with
+// r = RN(1/D) is the correctly rounded quotient for EVERY fp32 a (all 2^32 bit patterns compared with __fdiv_rn on the GPU,
+// tools/divconst_check.cu; subnormals, infinities and NaN included), 3 instructions instead of the ~9 of an IEEE division.
+// One value differs in representation only: a = -0.0 gives +0.0.  Not valid for non-integer divisors (0.45 fails 0.7 % of inputs).
+template <int D>
+VRGDG_HD float div_const(float a) {
+  static_assert(D == 9 || D == 25 || D == 49 || D == 81 || D == 255, "divisor not covered by the exhaustive check");
+  const float r = 1.0f / (float)D;
+#if defined(__CUDA_ARCH__)
+  const float q = __fmul_rn(a, r);
+  return __fmaf_rn(__fmaf_rn(-(float)D, q, a), r, q);
+#else
+  const float q = mulx(a, r);
+  return fmaf(fmaf(-(float)D, q, a), r, q);
+#endif
+}
+
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ----------------------------------
 struct U4 { uint32_t x, y, z, w; };
 
@@ -489,7 +506,7 @@ VRGDG_HD float stencil_epilogue_exact(int op, const float* n, float s) {
   switch (op) {
     case 1: {   // blur = (p00+p01+p02+p10+p11+p12+p20+p21+p22)/9.0, left to right ; out = img + s*(img - blur)
       float sum = addx(addx(addx(addx(addx(addx(addx(addx(n[0], n[1]), n[2]), n[3]), n[4]), n[5]), n[6]), n[7]), n[8]);
-      float blur = divx(sum, 9.0f);
+      float blur = div_const<9>(sum);                 // == sum / 9.0 (see div_const)
       v = addx(c, mulx(s, subx(c, blur)));
     } break;
     case 2: {   // lap = W + N + S + E - 4.0*img ; out = img + s*lap
