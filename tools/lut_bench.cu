@@ -203,6 +203,76 @@ __global__ void __launch_bounds__(256) k_lut_elem(const T* __restrict__ in, T* _
   }
 }
 
+// ---- variant 14: one lane per PIXEL as in the product, but the gather is cooperative: in round k the three lanes of a group
+// all work on the pixel of lane 3g+k (rgb broadcast by 3 shuffles), each loads ONE sector of that pixel's cell and interpolates
+// its channel; 3 shuffles hand the results back to the owner.  Same wavefront saving as v13 without a per-element data layout. ----
+template <typename T>
+__global__ void __launch_bounds__(256) k_lut_coop(const T* __restrict__ in, T* __restrict__ out, int64_t npix, const float* __restrict__ lute, int S) {
+  const float smax = (float)(S - 1);
+  const int lane = threadIdx.x & 31, grp3 = (lane / 3) * 3, ch = lane - grp3;
+  const int64_t nround = (npix + 29) / 30;                      // 30 pixels per warp pass (lanes 30, 31 idle)
+  const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * 256) >> 5;
+  for (int64_t w = warp0; w < nround; w += nwarps) {
+    const int64_t px = w * 30 + lane;
+    const bool own = lane < 30 && px < npix;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (own) { const T* s = in + px * 3; r = E<T>::ld(__ldg(s)); g = E<T>::ld(__ldg(s + 1)); b = E<T>::ld(__ldg(s + 2)); }
+    float res[3];
+    F8 q[3]; float fr[3], fg[3], fb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int src = min(grp3 + k, 31);
+      const float pr = __shfl_sync(0xffffffffu, r, src), pg = __shfl_sync(0xffffffffu, g, src), pb = __shfl_sync(0xffffffffu, b, src);
+      Idx c;
+      coord<false>(pr, smax, S, c.r0, c.r1, c.fr); coord<false>(pg, smax, S, c.g0, c.g1, c.fg); coord<false>(pb, smax, S, c.b0, c.b1, c.fb);
+      fr[k] = c.fr; fg[k] = c.fg; fb[k] = c.fb;
+      q[k] = ld256(lute + (size_t)((c.b0 * S + c.g0) * S + c.r0) * 24 + (ch < 3 ? ch : 0) * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const F8& a = q[k];
+      const float omb = 1.f - fb[k], omg = 1.f - fg[k], omr = 1.f - fr[k];
+      const float c00 = lerp1<true>(a.a.x, a.b.x, fb[k], omb), c10 = lerp1<true>(a.a.y, a.b.y, fb[k], omb);
+      const float c01 = lerp1<true>(a.a.z, a.b.z, fb[k], omb), c11 = lerp1<true>(a.a.w, a.b.w, fb[k], omb);
+      res[k] = clamp01(lerp1<true>(lerp1<true>(c00, c01, fg[k], omg), lerp1<true>(c10, c11, fg[k], omg), fr[k], omr));
+    }
+    // owner lane 3g+k needs channel c of round k from lane 3g+c
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int src = min(grp3 + c, 31);
+      const float v0 = __shfl_sync(0xffffffffu, res[0], src), v1 = __shfl_sync(0xffffffffu, res[1], src), v2 = __shfl_sync(0xffffffffu, res[2], src);
+      o[c] = ch == 0 ? v0 : (ch == 1 ? v1 : v2);
+    }
+    if (own) { T* d = out + px * 3; d[0] = E<T>::st(o[0]); d[1] = E<T>::st(o[1]); d[2] = E<T>::st(o[2]); }
+  }
+}
+
+template <typename T>
+void run_coop(const char* name, const char* tname, const T* in, T* out, int64_t npix, const float* le, int S, int sms, const char* dist, const T* check) {
+  auto kern = k_lut_coop<T>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+  int grid = sms * (occ > 0 ? occ : 1) * 4;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int i = 0; i < 2; ++i) kern<<<grid, 256>>>(in, out, npix, le, S);
+  CK(cudaDeviceSynchronize());
+  float best = 1e9f;
+  for (int i = 0; i < 5; ++i) {
+    CK(cudaEventRecord(a)); kern<<<grid, 256>>>(in, out, npix, le, S); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); best = fminf(best, ms);
+  }
+  size_t n = 3 << 18;
+  std::vector<T> h1(n), h2(n);
+  CK(cudaMemcpy(h1.data(), out, n * sizeof(T), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2.data(), check, n * sizeof(T), cudaMemcpyDeviceToHost));
+  double md = 0; for (size_t i = 0; i < n; ++i) md = fmax(md, fabs((double)(float)h1[i] - (double)(float)h2[i]));
+  double gpx = npix / (best * 1e-3) / 1e9;
+  printf("{\"variant\": \"%s\", \"dtype\": \"%s\", \"dist\": \"%s\", \"S\": %d, \"ms\": %.4f, \"Gpx/s\": %.1f, \"GB/s\": %.0f, \"occ\": %d, \"maxdiff_vs_v1\": %.3g}\n",
+         name, tname, dist, S, best, gpx, gpx * 6 * sizeof(T), occ, md);
+  fflush(stdout);
+}
+
 template <typename T, int STRIDE>
 void run_elem(const char* name, const char* tname, const T* in, T* out, int64_t npix, const float* le, int S, int sms, const char* dist, const T* check) {
   auto kern = k_lut_elem<T, STRIDE>;
@@ -344,6 +414,7 @@ template <typename T> void suite(const char* tname, int sms) {
       run<T, 11>("v11_cell_u21_2x256", tname, in, out, npix, l3, l4, lp, S, 0, sms, dist, ref, lc, lq);
       run_elem<T, 32>("v12_elem_planar_pad128", tname, in, out, npix, le32, S, sms, dist, ref);
       run_elem<T, 24>("v13_elem_planar_96", tname, in, out, npix, le24, S, sms, dist, ref);
+      run_coop<T>("v14_pixel_owner_3lane_coop", tname, in, out, npix, le24, S, sms, dist, ref);
       if (n * 12 <= 200 * 1024) run<T, 7>("v7_smem_scalar_exact", tname, in, out, npix, l3, l4, lp, S, n * 12, sms, dist, ref);
       if (n * 16 <= 200 * 1024) run<T, 8>("v8_smem_f4_exact", tname, in, out, npix, l3, l4, lp, S, n * 16, sms, dist, ref);
     }
