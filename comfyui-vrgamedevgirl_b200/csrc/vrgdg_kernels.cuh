@@ -330,13 +330,19 @@ template <typename T, int MASK> struct TileCfg {
 #ifndef VRGDG_HEAVY_NS
 #define VRGDG_HEAVY_NS (WORK ? 1 : 2)                 // in-place (fp32) tiles need the staged tile until the stencil is done
 #endif
-  static constexpr int MINB = HEAVY ? VRGDG_HEAVY_MINB : 2;
+#ifndef VRGDG_LIGHT_MINB
+#define VRGDG_LIGHT_MINB 2
+#endif
+#ifndef VRGDG_LIGHT_NS
+#define VRGDG_LIGHT_NS 3
+#endif
+  static constexpr int MINB = HEAVY ? VRGDG_HEAVY_MINB : VRGDG_LIGHT_MINB;
   static constexpr int COLS = TXE / VEC;              // threads across
   static constexpr int RG = (THREADS / COLS) >= 8 ? 8 : 4;   // row groups: COLS*RG active threads
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
-  static constexpr int NS = HEAVY ? VRGDG_HEAVY_NS : (GPLANE ? 2 : 3);   // pipeline stages
+  static constexpr int NS = HEAVY ? VRGDG_HEAVY_NS : (GPLANE ? 2 : VRGDG_LIGHT_NS);   // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
   static_assert(TY % RG == 0 && COLS * RG <= THREADS, "thread mapping");
