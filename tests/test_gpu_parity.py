@@ -780,3 +780,34 @@ def test_random_ragged_shapes_bit_exact_vs_oracle(pkg, cuda_device, oracle):
         b = pkg.ops.rgb_to_u8bgr(chain(pkg.ops.u8bgr_to_rgb(u8), ext_noise=zd))
         assert a.dtype == torch.uint8 and torch.equal(a, b), tag
     assert seen_tma                                                             # the list covers both loaders
+
+
+def test_batches_beyond_2G_elements_use_64bit_indexing(pkg, cuda_device):
+    """Maximum sizes (configs[2] / [3] are 6.4 G elements per call): 88 x 4K fp16 frames = 2.19 G elements > 2^31.  Every kernel
+    family must treat the LAST frames exactly as it treats them alone (absolute frame index passed for the grain)."""
+    nv = pkg._native
+    B, H, W = 88, 2160, 3840
+    assert B * H * W * 3 > 2 ** 31
+    x = torch.empty((B, H, W, 3), dtype=torch.float16, device=cuda_device)
+    gen = torch.Generator(device=cuda_device).manual_seed(7)
+    for b0 in range(0, B, 8):
+        x[b0:b0 + 8] = torch.rand((min(8, B - b0), H, W, 3), generator=gen, device=cuda_device, dtype=torch.float32).half()
+    tail = x[B - 2:].clone()
+    lut = _lut33(pkg)
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), lut=dict(lut_data=lut, strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    full = chain(x)                                                     # k_tile, TMA coordinates with a large frame index
+    assert nv.last_tile_path() == "tma"
+    assert torch.equal(full[B - 2:], chain(tail, first_frame=B - 2))
+    del full
+    g = pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=9)                        # k_point
+    assert torch.equal(g[B - 2:], pkg.ops.grain(tail, 0.04, 0.5, 0.5, seed=9, frame0=B - 2))
+    del g
+    u = pkg.ops.stencil3x3(x, nv.STENCIL_SOBEL_GPU, 0.3, nv.BORDER_ZERO)
+    assert torch.equal(u[B - 2:], pkg.ops.stencil3x3(tail, nv.STENCIL_SOBEL_GPU, 0.3, nv.BORDER_ZERO))
+    del u
+    sums = pkg.ops.lab_moments(x)                                       # per-frame reductions
+    assert torch.equal(sums[B - 2:], pkg.ops.lab_moments(tail))
+    params = pkg.ops.colormatch_params(sums, sums[:1].contiguous())
+    cm = pkg.ops.colormatch_apply(x, params, 1.0, 0.0)
+    assert torch.equal(cm[B - 2:], pkg.ops.colormatch_apply(tail, params[B - 2:].contiguous(), 1.0, 0.0))
