@@ -336,13 +336,16 @@ template <typename T, int MASK> struct TileCfg {
 #ifndef VRGDG_LIGHT_NS
 #define VRGDG_LIGHT_NS 3
 #endif
-  static constexpr int MINB = HEAVY ? VRGDG_HEAVY_MINB : VRGDG_LIGHT_MINB;
+  // plain stencils on 16-bit frames need few registers and 17 KB per staged tile: four CTAs per SM with a 2-stage ring
+  // (measured 395 -> 422 GPx/s on 1080p fp16; fp32 tiles are 35 KB per stage and gain nothing from a third CTA)
+  static constexpr bool SLIM = (MASK == 0) && (sizeof(T) == 2);
+  static constexpr int MINB = HEAVY ? VRGDG_HEAVY_MINB : (SLIM ? 4 : VRGDG_LIGHT_MINB);
   static constexpr int COLS = TXE / VEC;              // threads across
   static constexpr int RG = (THREADS / COLS) >= 8 ? 8 : 4;   // row groups: COLS*RG active threads
   static constexpr int RPT = TY / RG;                 // rows per thread
   static constexpr int PPR = TXE / 3 + 2;             // halo-tile pixels per row
   static constexpr int PAIRS = PPR / 2 + 1;           // generator pixel pairs covering them (tile x origin is even)
-  static constexpr int NS = HEAVY ? VRGDG_HEAVY_NS : (GPLANE ? 2 : VRGDG_LIGHT_NS);   // pipeline stages
+  static constexpr int NS = HEAVY ? VRGDG_HEAVY_NS : ((GPLANE || SLIM) ? 2 : VRGDG_LIGHT_NS);   // pipeline stages
   static constexpr int STAGE_BYTES = ROWS * BX * (int)sizeof(T);
   static_assert(PADL + TXE + 3 <= BX, "box too narrow");
   static_assert(TY % RG == 0 && COLS * RG <= THREADS, "thread mapping");
