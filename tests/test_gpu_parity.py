@@ -811,3 +811,29 @@ def test_batches_beyond_2G_elements_use_64bit_indexing(pkg, cuda_device):
     params = pkg.ops.colormatch_params(sums, sums[:1].contiguous())
     cm = pkg.ops.colormatch_apply(x, params, 1.0, 0.0)
     assert torch.equal(cm[B - 2:], pkg.ops.colormatch_apply(tail, params[B - 2:].contiguous(), 1.0, 0.0))
+
+
+def test_enhance_frames_bytes_in_bytes_out(pkg, cuda_device, oracle):
+    """The enhancer's per-batch data path (EnhancerNodes.py:415-420) fused on the device == the four helpers called one after the
+    other (bytes), and == the oracle for the deterministic part (Lanczos4 -> /255 -> unsharp -> truncating encode)."""
+    import importlib
+    vt = importlib.import_module("comfyui-vrgamedevgirl_b200.video_tools")
+    rng = np.random.default_rng(21)
+    frames = [rng.integers(0, 256, (90, 160, 3), dtype=np.uint8) for _ in range(5)]
+    st = {"sharpen_enabled": True, "sharpen_strength": 0.6, "grain_enabled": True, "grain_intensity": 0.05, "saturation_mix": 0.4, "seed": 77,
+          "use_gpu": False}
+    before = pkg._native.launch_count()
+    fused = vt.enhance_frames(frames, 240, 136, st, frame_start=12)
+    assert pkg._native.launch_count() == before + 3                                 # Lanczos h + v, unsharp + grain on the bytes
+    steps = vt._tensor_to_frames(vt._apply_effects_batch(vt._frames_to_tensor(vt._resize_frames(frames, 240, 136)), st, 12))
+    assert len(fused) == 5 and all(np.array_equal(a, b) for a, b in zip(fused, steps))
+    nograin = dict(st, grain_enabled=False)
+    got = vt.enhance_frames(frames, 240, 136, nograin, 0)
+    ref = oracle.tensor_to_frames(oracle.effects_batch(oracle.frames_to_tensor(oracle.resize_frames(frames, 240, 136)), nograin, 0))
+    assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    same = vt.enhance_frames(frames, 160, 90, dict(nograin, use_gpu=True), 0)       # no resize, torch-path border
+    ref2 = oracle.tensor_to_frames(oracle.unsharp_torch(oracle.frames_to_tensor(frames), 0.6))     # avg_pool2d path (:240-250)
+    assert all(np.array_equal(a, b) for a, b in zip(same, ref2))
+    assert vt.enhance_frames([], 10, 10, st) == []
+    mixed = vt.enhance_frames([frames[0], frames[1][:45]], 80, 46, nograin, 0)      # mixed sizes: helper-by-helper route
+    assert mixed[0].shape == mixed[1].shape == (46, 80, 3)
