@@ -67,3 +67,25 @@ def test_sass_contains_tma_and_no_legacy_tensor_paths(pkg):
         pytest.skip("cuobjdump not installed")
     lst = subprocess.run([cuobjdump, "-lelf", pkg._native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in lst and "sm_90" not in lst and "sm_80" not in lst
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_structs(pkg, tmp_path):
+    """include/vrgdg_b200.h must compile as C99 on its own (the boundary is a C ABI, not C++), and the descriptor structs must have
+    the size the ctypes mirrors in _native.py assume (a silent mismatch would shift every field after it)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "vrgdg_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "vrgdg_b200.h"\nint main(void) { printf("%zu %zu %zu\\n", sizeof(vrgdg_chain_desc), '
+                   'sizeof(vrgdg_adjust_desc), sizeof(vrgdg_resize_desc)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    nv = pkg._native
+    assert sizes == [ctypes.sizeof(nv.ChainDesc), ctypes.sizeof(nv.AdjustDesc), ctypes.sizeof(nv.ResizeDesc)]
