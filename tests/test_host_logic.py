@@ -219,3 +219,45 @@ def test_lanczos4_host_tables_match_the_oracle(pkg, oracle):
     assert np.array_equal(ofs, np.arange(64)) and np.array_equal(coef, np.tile(np.array([0, 0, 0, 2048, 0, 0, 0, 0], np.int16), (64, 1)))
     assert lib.vrgdg_lanczos4_tables(0, 4, ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p)) == -1
     assert lib.vrgdg_lanczos4_scratch_bytes(2, 10, 7) == 2 * 10 * 7 * 3 * 4
+
+
+def test_random_cube_files_and_lanczos_tables_fuzz(pkg, oracle, tmp_path):
+    """Seeded fuzz of the two host-side table builders against the oracle: .cube text with random whitespace / comments / keyword
+    lines / exponent notation / non-unit domains (product parser == oracle parser == the values written), and Lanczos4 tables for
+    random size pairs (the library's host code == the oracle's restatement of OpenCV)."""
+    import ctypes
+    rng = np.random.default_rng(99)
+    for n in range(12):
+        S = int(rng.integers(2, 7))
+        vals = rng.random((S, S, S, 3)).astype(np.float32) * float(rng.choice([1.0, 2.0, 0.5])) - float(rng.choice([0.0, 0.25]))
+        lines = ["# fuzz %d" % n, 'TITLE "t %d"' % n, ("LUT_3D_SIZE %d" % S) if n % 2 else ("LUT_3D_SIZE\t%d  " % S)]
+        dom = n % 3 == 0
+        if dom:
+            lines += ["DOMAIN_MIN -0.25 0 0.5", "DOMAIN_MAX 1.5 1 2e0"]
+        if n % 4 == 1:
+            lines += ["LUT_3D_INPUT_RANGE 0.0 1.0 2.0", "SOMETHING else entirely here 1 2"]     # not 3 tokens -> skipped like the reference
+        for i, v in enumerate(vals.reshape(-1, 3)):
+            fmt = ("%.6f %.6f %.6f", "%.9g\t%.9g   %.9g", "  %e %e %e  ")[(n + i) % 3]
+            lines.append(fmt % tuple(float(c) for c in v))
+            if i % 11 == 5:
+                lines += ["", "# comment in the table"]
+        path = tmp_path / ("fuzz %d.cube" % n)
+        path.write_text("\n".join(lines) + "\n")
+        a, b = pkg.VRGDG_LUTS._parse_cube_file(str(path)), oracle.parse_cube(str(path))
+        assert a["size"] == b["size"] == S and torch.equal(a["lut"], b["lut"])
+        assert torch.equal(a["domain_min"], b["domain_min"]) and torch.equal(a["domain_max"], b["domain_max"])
+        assert a["domain_max"].tolist() == ([1.5, 1.0, 2.0] if dom else [1.0, 1.0, 1.0])
+        assert np.abs(a["lut"].numpy() - vals).max() <= 1e-6                 # %.6f rounding at most; red fastest order preserved
+    bad = tmp_path / "three_token_keyword.cube"                              # a 3-token non-numeric line is read as data by the reference
+    bad.write_text("LUT_3D_SIZE 2\nLUT_3D_INPUT_RANGE 0.0 1.0\n" + "0 0 0\n" * 8)
+    for parse in (pkg.VRGDG_LUTS._parse_cube_file, oracle.parse_cube):
+        with pytest.raises(ValueError):
+            parse(str(bad))
+    lib = pkg._native.load_library()
+    for _ in range(25):
+        s_, d_ = int(rng.integers(1, 1500)), int(rng.integers(1, 1500))
+        ofs, coef = np.empty(d_, np.int32), np.empty((d_, 8), np.int16)
+        assert lib.vrgdg_lanczos4_tables(s_, d_, ofs.ctypes.data_as(ctypes.c_void_p), coef.ctypes.data_as(ctypes.c_void_p)) == 0
+        o2, c2 = oracle.lanczos4_tables(s_, d_)
+        assert np.array_equal(ofs, o2) and np.array_equal(coef, c2), (s_, d_)
+        assert int(np.abs(coef.astype(np.int32).sum(axis=1) - 2048).max()) <= 3     # weights sum to 1 in fixed point, up to rounding
