@@ -39,9 +39,10 @@ VRGDG_HD float sqrtx(float a) { return sqrtf(a); }
 VRGDG_HD float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
 // a / D for the integer constants the exact kernels divide by (9, 25, 49, 81, 255): q = a*r, q' = fma(fma(-D, q, a), r, q) with
-// r = RN(1/D) is the correctly rounded quotient for EVERY fp32 a (all 2^32 bit patterns compared with __fdiv_rn on the GPU,
-// tools/divconst_check.cu; subnormals, infinities and NaN included), 3 instructions instead of the ~9 of an IEEE division.
-// One value differs in representation only: a = -0.0 gives +0.0.  Not valid for non-integer divisors (0.45 fails 0.7 % of inputs).
+// r = RN(1/D) is the correctly rounded quotient for every FINITE fp32 a (all finite bit patterns, subnormals included, compared
+// with __fdiv_rn on the GPU: tools/divconst_check.cu), 3 instructions instead of the ~9 of an IEEE division.  Outside that:
+// a = -0.0 gives +0.0 (equal value) and a = +-inf gives NaN (inf - inf in the residual); sums of frame values are finite.
+// Not valid for non-integer divisors (0.45 fails 0.7 % of inputs).
 template <int D>
 VRGDG_HD float div_const(float a) {
   static_assert(D == 9 || D == 25 || D == 49 || D == 81 || D == 255, "divisor not covered by the exhaustive check");

@@ -79,6 +79,11 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
   delete[] packed;
 }
 
+void hc_div_const(const float* in, float* out, int64_t n, int d) {
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = d == 9 ? div_const<9>(in[i]) : (d == 25 ? div_const<25>(in[i]) : (d == 49 ? div_const<49>(in[i]) : (d == 81 ? div_const<81>(in[i]) : div_const<255>(in[i]))));
+}
+
 void hc_rgb_to_lab(const float* in, float* out, int64_t n) {
   for (int64_t i = 0; i < n; ++i) rgb_to_lab(in[3 * i], in[3 * i + 1], in[3 * i + 2], out[3 * i], out[3 * i + 1], out[3 * i + 2]);
 }

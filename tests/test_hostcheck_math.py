@@ -140,3 +140,24 @@ def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
         assert np.abs(out - flat(c["out_t100"][b])).max() <= 1e-5
         hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 0.6, 1.0 - 0.6)
         assert np.abs(out - flat(c["out_t60"][b])).max() <= 1e-5
+
+
+def test_div_const_is_the_correctly_rounded_quotient(hostcheck):
+    """div_const<D> (3 instructions: q = a*r, q' = fma(fma(-D, q, a), r, q)) against IEEE division on 8 M random finite bit patterns per
+    divisor plus the special values; the GPU-side exhaustive run over all 2^32 patterns is tools/divconst_check.cu
+    (profiles/r01_final_v2/divconst_exhaustive_check.jsonl).  The one representational difference: -0.0 -> +0.0."""
+    hostcheck.hc_div_const.argtypes = [vp, vp, i64, ci]
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2 ** 32, size=8_000_000, dtype=np.uint64).astype(np.uint32)
+    special = np.array([0x00000000, 0x00000001, 0x007FFFFF, 0x00800000, 0x7F7FFFFF, 0xFF7FFFFF, 0x3F800000, 0x41100000, 0x80000001], dtype=np.uint32)
+    x = np.concatenate([bits, special]).view(np.float32)
+    x = x[np.isfinite(x)]                                                   # finite inputs only: +-inf gives NaN (documented in div_const)
+    o = np.empty_like(x)
+    with np.errstate(all="ignore"):
+        for d in (9, 25, 49, 81, 255):
+            hostcheck.hc_div_const(P(x), P(o), x.shape[0], d)
+            ref = x / np.float32(d)
+            assert np.array_equal(o.view(np.uint32), ref.view(np.uint32)), d
+    z = np.array([-0.0], dtype=np.float32)
+    hostcheck.hc_div_const(P(z), P(o), 1, 9)
+    assert o[0] == 0.0                                                      # value equal; the sign of zero is not preserved

@@ -1,4 +1,4 @@
-// Exhaustive check (all 2^32 fp32 bit patterns) that  q = a*r; q' = fma(fma(-d, q, a), r, q)  with r = RN(1/d) equals the
+// Exhaustive check (all 2^32 fp32 bit patterns; NaN and +-inf inputs are routed to the division by the guard) that  q = a*r; q' = fma(fma(-d, q, a), r, q)  with r = RN(1/d) equals the
 // correctly rounded a / d for the constant divisors the exact kernels use.  nvcc -arch=sm_100a -O3 tools/divconst_check.cu
 #include <cstdio>
 #include <cstdint>
