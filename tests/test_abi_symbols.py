@@ -89,3 +89,40 @@ def test_header_is_plain_c_and_matches_the_ctypes_structs(pkg, tmp_path):
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     nv = pkg._native
     assert sizes == [ctypes.sizeof(nv.ChainDesc), ctypes.sizeof(nv.AdjustDesc), ctypes.sizeof(nv.ResizeDesc)]
+
+
+def test_argument_validation_of_the_widened_entry_points_needs_no_gpu(pkg):
+    """resize / blend / Lanczos / adjust reject bad arguments with VRGDG_E_INVALID (-> ValueError) and a message naming the entry point,
+    before any CUDA call (so this runs on the CPU-only build box too)."""
+    import ctypes
+    nv = pkg._native
+    lib = nv.load_library()
+    one = ctypes.c_void_p(16)                                     # a non-null, never dereferenced pointer
+    rd = nv.ResizeDesc(2, 0, 0, 8, 8, 16, 16, 0, 0)
+    cases = [
+        (lambda: lib.vrgdg_resize(one, ctypes.c_void_p(32), 1, 8, 8, 3, 16, 16, 0, None, None), b"vrgdg_resize"),                    # null descriptor
+        (lambda: lib.vrgdg_resize(one, ctypes.c_void_p(32), 1, 8, 8, 2, 16, 16, 0, ctypes.byref(rd), None), b"channels"),
+        (lambda: lib.vrgdg_resize(one, ctypes.c_void_p(32), 1, 8, 8, 3, 16, 16, 3, ctypes.byref(rd), None), b"float dtype"),         # uint8 frames
+        (lambda: lib.vrgdg_resize(one, ctypes.c_void_p(32), 1, 8, 8, 3, 16, 16, 0, ctypes.byref(nv.ResizeDesc(9, 0, 0, 8, 8, 16, 16, 0, 0)), None), b"mode"),
+        (lambda: lib.vrgdg_resize(one, ctypes.c_void_p(32), 1, 8, 8, 3, 16, 16, 0, ctypes.byref(nv.ResizeDesc(2, 4, 0, 8, 8, 16, 16, 0, 0)), None), b"ROI"),
+        (lambda: lib.vrgdg_resize(one, one, 1, 8, 8, 3, 16, 16, 0, ctypes.byref(rd), None), b"in-place"),
+        (lambda: lib.vrgdg_blend(one, one, one, -1, 0, 0.5, 0.5, None), b"vrgdg_blend"),
+        (lambda: lib.vrgdg_blend(None, one, one, 4, 0, 0.5, 0.5, None), b"null"),
+        (lambda: lib.vrgdg_lanczos4_resize_u8(one, ctypes.c_void_p(32), 1, 8, 8, 16, 16, None, None, None, None, None, 0, None), b"null"),
+        (lambda: lib.vrgdg_lanczos4_resize_u8(one, ctypes.c_void_p(32), 1, 0, 8, 16, 16, one, one, one, one, one, 1 << 20, None), b"empty source"),
+        (lambda: lib.vrgdg_lanczos4_resize_u8(one, ctypes.c_void_p(32), 1, 8, 8, 16, 16, one, one, one, one, one, 4, None), b"scratch too small"),
+        (lambda: lib.vrgdg_adjust(one, ctypes.c_void_p(32), 1, 8, 8, 0, None, None, None, None, 0, None), b"vrgdg_adjust"),
+    ]
+    for call, needle in cases:
+        rc = call()
+        assert rc == nv.E_INVALID and needle in lib.vrgdg_last_error(), (rc, needle, lib.vrgdg_last_error())
+    # the message belongs to the LAST failing call on this thread
+    assert b"vrgdg_adjust" in lib.vrgdg_last_error()
+    rc = lib.vrgdg_blend(None, one, one, 4, 0, 0.5, 0.5, None)
+    assert rc == nv.E_INVALID and b"vrgdg_blend" in lib.vrgdg_last_error()
+    with pytest.raises(ValueError):
+        nv.check(rc)
+    # zero-sized work is a successful no-op before any CUDA call
+    assert lib.vrgdg_resize(None, None, 0, 8, 8, 3, 16, 16, 0, ctypes.byref(rd), None) == 0
+    assert lib.vrgdg_blend(None, None, None, 0, 0, 0.5, 0.5, None) == 0
+    assert lib.vrgdg_lanczos4_resize_u8(None, None, 0, 8, 8, 16, 16, None, None, None, None, None, 0, None) == 0
