@@ -5,7 +5,6 @@ VRGDG_VideoEnhanceRestore :404-418).  F.interpolate + crop / F.pad + clamp becom
 changes the ROI, the resampled size and the placement offset handed to the kernel.  The LTX sampling between prepare and restore,
 the context dict and the logging are the reference's control plane and stay out of scope.
 """
-import torch
 
 from . import ops
 from ._runtime import compute_device

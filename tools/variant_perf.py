@@ -1,7 +1,6 @@
 """Times the headline fused chain (grain -> 33^3 LUT -> unsharp, fp16 1080p) for every library under lib/variants plus the stock
 one (GPU box only; tuning experiments).  python tools/variant_perf.py [frames] [chain|unsharp_f16|unsharp_f32]"""
 import glob
-import json
 import os
 import subprocess
 import sys
