@@ -1,14 +1,18 @@
-"""bench.py — headline benchmark of the post-processing hot path (driver contract: see DESIGN.md "Measurement").
+"""bench.py — headline benchmark of the post-processing hot path (driver contract: DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload = BASELINE.json configs[1]: fused grain + 33^3 .cube LUT + unsharp on 64 x 1920 x 1080 fp16 frames per GPU
-(weak scaling: every rank owns 64 frames; frames are independent, no data-path collective).
-One "step" = one pass of the fused chain over the rank's 64 frames = ONE kernel launch (k_tile).
-  value : MP/s, frames resident in HBM (CUDA events, max over ranks)
-  e2e   : MP/s through the public API (PostChain.run_host) from pinned HOST frames to pinned HOST frames, H2D and
-          D2H copies inside the timed region
+Headline workload = the configuration BASELINE.json's metric is quoted on ("grain+LUT+colormatch+sharpen chain at 4K"), i.e. the
+per-GPU shard of configs[3]: grain(I=.04, s=.5, seed 42) -> colour match(t=1, one 4K reference frame) -> 33^3 .cube LUT ->
+unsharp(.5) on 128 x 3840x2160 fp32 frames per GPU, synthesised on the device (weak scaling: every rank owns 128 frames).
+One "step" = one pass of the chain over the rank's frames:
+    reference moments (k_lab_moments on the rank's row shard + ONE NCCL all-gather of 56 bytes per rank, dist.py)
+    -> per-frame moments of the grained frames (k_lab_moments, grain recomputed) -> k_colormatch_params -> k_tile (fused apply)
+  value : MP/s, frames resident in HBM (CUDA events around K steps on the launching stream, max over ranks)
+  e2e   : MP/s through the public API (PostChain.run_host) from pinned HOST frames to pinned HOST frames on a stated sub-batch,
+          H2D and D2H copies inside the timed region; e2e.stock_nodes = the same chain as four unchanged ComfyUI nodes
+  extra : configs[1] (64 x 1080p fp16, grain + LUT + unsharp) and "grain + LUT + unsharp at 4K fp32", each with its own roofline
   --impl reference : the reference's CPU path for the same chain (oracle port of the reference nodes; /root/reference
           does not exist on the GPU box) on all host cores, rank 0 only, bounded sample per step
 """
@@ -24,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
+
 
 def host_threads():
     """Threads for the CPU arm: one per PHYSICAL core (torch's own default; measured on the GPU box: 128 SMT threads run the
@@ -44,11 +49,15 @@ import torch  # noqa: E402
 
 PKG = "comfyui-vrgamedevgirl_b200"
 LUT_FILE = os.path.join(ROOT, PKG, "LUTS", "B200 Vintage 33.cube")
-FRAMES, H, W = 64, 1080, 1920
 GRAIN = dict(intensity=0.04, saturation_mix=0.5, seed=42)
 SHARPEN = 0.5
-METRIC = "megapixels/sec"
-WORKLOAD = "configs[1]: fused grain + 33^3 .cube LUT + unsharp, 64x1920x1080 fp16 frames per GPU"
+METRIC = "megapixels/sec (grain+LUT+colormatch+sharpen chain) at 4K"
+H4K, W4K = 2160, 3840
+FRAMES_4K = int(os.environ.get("VRGDG_BENCH_FRAMES", "128"))       # per GPU (configs[3]: 1024 frames over 8 GPUs)
+E2E_FRAMES = 16                                                      # sub-batch of the end-to-end leg (1.6 GB each way)
+STOCK_FRAMES = 4                                                     # sub-batch of the stock-node leg
+WORKLOAD = ("configs[3] per-GPU shard: grain -> colour match (one 4K reference, t=1) -> 33^3 .cube LUT -> unsharp, "
+            "%d x 3840x2160 fp32 frames per GPU" % FRAMES_4K)
 
 
 def measured_peaks():
@@ -59,14 +68,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def recorded_traffic(key):
+    """dram bytes per launch of a kernel from the committed ncu capture (profiles/dominant_kernel.json), with a staleness flag:
+    the capture is only valid for the kernel sources it was taken from (content hash of csrc/ + the header)."""
     path = os.path.join(ROOT, "profiles", "dominant_kernel.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            d = json.load(fh)
-        return d.get("dram_bytes_per_launch"), d
-    return None, None
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as fh:
+        d = json.load(fh).get(key)
+    if not d:
+        return None, None
+    try:
+        cur = importlib.import_module(PKG + ".build")._source_hash()
+    except Exception:
+        cur = None
+    return d.get("dram_bytes_per_launch"), {"capture": d.get("capture"), "traffic_stale": bool(cur is None or d.get("src_hash") != cur)}
 
 
 class ClockSampler(threading.Thread):
@@ -109,31 +125,59 @@ class ClockSampler(threading.Thread):
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def cpu_chain_sample(frames, steps=1, threads=None):
-    """The reference's CPU path for the same chain (oracle port, fp32 as users run it) on `frames` 1080p frames.
-    Returns (MP/s, seconds, threads)."""
+def device_natural_frames(n, h, w, seed, dtype, dev):
+    """helpers.natural_frames (SURVEY 8d distribution N: 4 octaves of bilinearly upsampled uniform noise + 2 % white noise),
+    generated on the device; every frame gets its own gain / offset so that per-frame colour statistics differ (config 3)."""
+    g = torch.Generator(device=dev).manual_seed(1000 + seed)
+    acc = torch.zeros(n, 3, h, w, device=dev)
+    amp, tot = 1.0, 0.0
+    for o in range(4):
+        base = torch.rand(n, 3, 8 * 2 ** o + 1, 15 * 2 ** o + 1, generator=g, device=dev)
+        acc += amp * torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=True)
+        tot += amp
+        amp *= 0.5
+    acc /= tot
+    acc += 0.02 * (torch.rand(n, 3, h, w, generator=g, device=dev) - 0.5)
+    acc += torch.tensor([0.03, 0.0, -0.03], device=dev).view(1, 3, 1, 1)
+    gain = 0.8 + 0.4 * torch.rand(n, 1, 1, 1, generator=g, device=dev)
+    off = 0.1 * (torch.rand(n, 3, 1, 1, generator=g, device=dev) - 0.5)
+    return (acc * gain + off).clamp_(0, 1).permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def tile_frames(base, total):
+    """`total` frames from the distinct `base` frames (repeated; a per-frame offset keeps every frame's statistics distinct)"""
+    n = base.shape[0]
+    x = base.repeat((total + n - 1) // n, 1, 1, 1)[:total].contiguous()
+    x += (torch.arange(total, device=x.device, dtype=torch.float32).view(-1, 1, 1, 1) * (0.02 / max(total, 1))).to(x.dtype)
+    return x.clamp_(0, 1)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own nodes (oracle port) for the same chain
+# ------------------------------------------------------------------------------------------------------------------------
+def cpu_full_chain(frames, steps, threads=None):
+    """grain -> colour match -> LUT -> unsharp (numpy path) on `frames` 4K fp32 frames.  Returns (MP/s, best seconds, threads)."""
     import vrgdg_oracle as oracle
     from helpers import natural_frames
     if threads:
         torch.set_num_threads(threads)
-    x = natural_frames(frames, H, W, seed=0)
+    x = natural_frames(frames, H4K, W4K, seed=0)
+    ref = natural_frames(1, H4K, W4K, seed=99)
     lut = oracle.parse_cube(LUT_FILE)
     best = None
     for _ in range(steps):
         torch.manual_seed(123)
         t0 = time.perf_counter()
         a = oracle.film_grain(x, GRAIN["intensity"], GRAIN["saturation_mix"], batch_size=4)
-        b = oracle.apply_lut(a, lut, 10.0)
-        oracle.unsharp_numpy(b, SHARPEN)
+        b = oracle.color_match(a, ref, 1.0, 1)
+        c = oracle.apply_lut(b, lut, 10.0)
+        oracle.unsharp_numpy(c, SHARPEN)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return frames * H * W / 1e6 / best, best, torch.get_num_threads()
+    return frames * H4K * W4K / 1e6 / best, best, torch.get_num_threads()
 
 
 def run_reference(args):
@@ -142,25 +186,27 @@ def run_reference(args):
         return
     threads = host_threads()
     torch.set_num_threads(threads)
-    sample_frames = 4
+    sample_frames = 2
     import vrgdg_oracle as oracle
     from helpers import natural_frames
-    x = natural_frames(sample_frames, H, W, seed=0)
+    x = natural_frames(sample_frames, H4K, W4K, seed=0)
+    ref = natural_frames(1, H4K, W4K, seed=99)
     lut = oracle.parse_cube(LUT_FILE)
 
     def step():
         a = oracle.film_grain(x, GRAIN["intensity"], GRAIN["saturation_mix"], batch_size=4)
-        b = oracle.apply_lut(a, lut, 10.0)
-        return oracle.unsharp_numpy(b, SHARPEN)
-    for _ in range(max(1, min(args.warmup, 1))):
-        step()
-    steps = max(1, min(args.steps, 5))
+        b = oracle.color_match(a, ref, 1.0, 1)
+        c = oracle.apply_lut(b, lut, 10.0)
+        return oracle.unsharp_numpy(c, SHARPEN)
+    step()
+    steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    mps = sample_frames * H * W / 1e6 / dt
-    sample = "%d x 1080p fp32 frames per step (reference CPU nodes FastFilmGrain -> VRGDG_LUTS -> FastUnsharpSharpen numpy path; fp16 on CPU is not what users run)" % sample_frames
+    mps = sample_frames * H4K * W4K / 1e6 / dt
+    sample = ("%d x 3840x2160 fp32 frames per step through the reference CPU nodes FastFilmGrain -> ColorMatchToReference -> VRGDG_LUTS -> "
+              "FastUnsharpSharpen (numpy path), oracle port" % sample_frames)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(mps, 3), "unit": "MP/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
         "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -170,8 +216,13 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------------
 def run_b200(args):
     rank, world, local = dist_env()
+    pkg = importlib.import_module(PKG)
+    numa_cpus = pkg._runtime.bind_to_gpu_numa(local)        # before any pinned allocation / first touch
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -180,23 +231,12 @@ def run_b200(args):
         dist = None
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    pkg = importlib.import_module(PKG)
     nv = pkg._native
     nv.load_library()
-    from helpers import natural_frames
-
-    # synthetic clip, generated on the device; rank r owns absolute frames [r*FRAMES, (r+1)*FRAMES)
-    base = natural_frames(8, H, W, seed=rank, dtype=torch.float16, device=dev)
-    x = base.repeat(FRAMES // 8, 1, 1, 1).contiguous()
-    x += (torch.rand(FRAMES, 1, 1, 1, device=dev) * 0.02).half()
-    x.clamp_(0, 1)
-    del base
-    out = torch.empty_like(x)
+    vdist = importlib.import_module(PKG + ".dist")
+    peak, peak_src = measured_peaks()
     lut = pkg.VRGDG_LUTS._parse_cube_file(LUT_FILE)
-    chain = pkg.chain.PostChain(grain=GRAIN, lut=dict(lut_data=lut, strength=10.0),
-                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=SHARPEN, border=nv.BORDER_REPLICATE), device=dev)
-    first = rank * FRAMES
-    npix = FRAMES * H * W
+    stencil = dict(op=nv.STENCIL_BOX_UNSHARP, strength=SHARPEN, border=nv.BORDER_REPLICATE)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -204,75 +244,188 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(ms):
+    def max_over_ranks(v):
         if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
+    def timed(fn, steps, warmup):
+        """W untimed + K timed calls bracketed by barrier + synchronize; device time from CUDA events on the launching stream."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = nv.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, nv.launch_count() - l0
+
+    # ---- headline: configs[3] shard, frames synthesised on the device ----
+    first = rank * FRAMES_4K                                  # absolute index of this rank's first frame (keys the grain)
+    x = tile_frames(device_natural_frames(8, H4K, W4K, seed=rank, dtype=torch.float32, dev=dev), FRAMES_4K)
+    out = torch.empty_like(x)
+    ref = device_natural_frames(1, H4K, W4K, seed=4242, dtype=torch.float32, dev=dev)      # the same reference frame on every rank
+    chain = pkg.chain.PostChain(grain=GRAIN, colormatch=dict(ref_sums=vdist.reference_sums_distributed(ref), strength=1.0),
+                                lut=dict(lut_data=lut, strength=10.0), stencil=stencil, device=dev)
+    npix = FRAMES_4K * H4K * W4K
+    warm = max(args.warmup, 3)
+
+    def step():
+        # the path's one collective: reference rows sharded over the ranks, 7 doubles all-gathered, folded in rank order
+        chain.set_reference(ref_sums=vdist.reference_sums_distributed(ref))
         chain(x, first_frame=first, out=out)
+
     sampler = ClockSampler(local)
+    for _ in range(warm):
+        step()
     barrier()
     sampler.start()
-    launches0 = nv.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        chain(x, first_frame=first, out=out)
-    e1.record()
-    barrier()
-    launches = nv.launch_count() - launches0
+    chain.timing = []                                         # CUDA events around the moments pass and the fused apply kernel
+    ms_step, launches = timed(step, args.steps, 0)
     sampler.stop_flag.set()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
+    seg = chain.timing
+    chain.timing = None
+    ms_moments = max_over_ranks(sum(a.elapsed_time(b) for a, b, _, _ in seg) / len(seg))
+    ms_apply = max_over_ranks(sum(c.elapsed_time(d) for _, _, c, d in seg) / len(seg))
     value = world * npix / 1e6 / (ms_step / 1e3)
     tile_path = nv.last_tile_path()
+    ref_sums_identical = True
+    if dist is not None:                                      # every rank holds bit-identical reference statistics
+        mine = chain._ref_sums.reshape(-1).contiguous()
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        ref_sums_identical = all(torch.equal(a, allr[0]) for a in allr)
 
-    # ---- end to end through the public API: pinned host frames -> pinned host frames ----
-    host_in = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
-    host_in.copy_(x)
+    def roofline(alg_bytes, ms, extra=None):
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        d = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "peak_source": peak_src,
+             "algorithmic_bytes_per_launch": alg_bytes}
+        d.update(extra or {})
+        return d
+
+    # ---- extra lines: the gather-bound chains without colour match ----
+    extras = {}
+    if not args.no_extra:
+        ex_steps = max(3, min(args.steps, 10))
+        x4 = x[:32]
+        o4 = out[:32]
+        c4 = pkg.chain.PostChain(grain=GRAIN, lut=dict(lut_data=lut, strength=10.0), stencil=stencil, device=dev)
+        ms4, _ = timed(lambda: c4(x4, first_frame=first, out=o4), ex_steps, 3)
+        n4 = 32 * H4K * W4K
+        extras["grain_lut_unsharp_4k_f32"] = {
+            "workload": "fused grain + 33^3 LUT + unsharp, 32 x 3840x2160 fp32 frames per GPU, one k_tile launch per step",
+            "value": round(world * n4 / 1e6 / (ms4 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms4, 4), "steps": ex_steps,
+            "roofline": roofline(n4 * 24, ms4, {"kernel": "k_tile<float, grain|lut>"})}
+        x2 = tile_frames(device_natural_frames(8, 1080, 1920, seed=rank, dtype=torch.float16, dev=dev), 64)
+        o2 = torch.empty_like(x2)
+        ms2, _ = timed(lambda: c4(x2, first_frame=rank * 64, out=o2), ex_steps, 3)
+        n2 = 64 * 1080 * 1920
+        tr2, st2 = recorded_traffic("configs1_f16")
+        extras["configs1_grain_lut_unsharp_1080p_f16"] = {
+            "workload": "configs[1]: fused grain + 33^3 LUT + unsharp, 64 x 1920x1080 fp16 frames per GPU, one k_tile launch per step",
+            "value": round(world * n2 / 1e6 / (ms2 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms2, 4), "steps": ex_steps,
+            "roofline": roofline(n2 * 12, ms2, dict({"kernel": "k_tile<half, grain|lut>", "traffic": tr2}, **(st2 or {})))}
+        del x2, o2, c4
+
+    # ---- end to end through the public API: pinned host frames -> pinned host frames (sub-batch) ----
+    nE = min(E2E_FRAMES, FRAMES_4K)
+    host_in = torch.empty((nE,) + tuple(x.shape[1:]), dtype=x.dtype, pin_memory=True)
+    host_in.copy_(x[:nE])
+    host_out = torch.empty_like(host_in, pin_memory=True)      # pinned once, reused every step
     e2e_steps = max(1, min(args.steps, 5))
-    host_out = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)      # pinned once, reused every step
-    chain.run_host(host_in, chunk_frames=8, first_frame=first, out=host_out)      # warm-up
+    chunk = int(os.environ.get("VRGDG_BENCH_CHUNK", "2"))
+
+    def e2e_step():
+        chain.set_reference(ref_sums=vdist.reference_sums_distributed(ref))
+        return chain.run_host(host_in, chunk_frames=chunk, first_frame=first, out=host_out)
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
     checksum = 0.0
     for _ in range(e2e_steps):
-        res = chain.run_host(host_in, chunk_frames=8, first_frame=first, out=host_out)
-        checksum += float(res[0, 0, 0, 0])          # device->host result is read on the host
+        res = e2e_step()
+        checksum += float(res[0, 0, 0, 0])                     # the device->host result is read on the host
     torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    e2e_ms = max_over_ranks(e2e_ms)
-    e2e_value = world * npix / 1e6 / (e2e_ms / 1e3)
-    frame_bytes = x.numel() * x.element_size()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e_value = world * nE * H4K * W4K / 1e6 / (e2e_ms / 1e3)
+    e2e_bytes = host_in.numel() * host_in.element_size()
+
+    def copy_gbs(dst, src):
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return src.numel() * src.element_size() / (time.perf_counter() - t) / 1e9
+    d_tmp = torch.empty_like(host_in, device=dev)
+    copy_gbs(d_tmp, host_in)
+    h2d, d2h = copy_gbs(d_tmp, host_in), copy_gbs(host_out, d_tmp)
+    del d_tmp
+
+    # ---- the same chain as four unchanged ComfyUI nodes on pageable host tensors (what a saved workflow pays) ----
+    stock = None
+    if not args.no_extra:
+        nS = min(STOCK_FRAMES, FRAMES_4K)
+        hx, hr = x[:nS].cpu(), ref.cpu()
+        nodes = (pkg.FastFilmGrain(), pkg.ColorMatchToReference(), pkg.VRGDG_LUTS(), pkg.FastUnsharpSharpen())
+
+        def stock_step():
+            a = nodes[0].apply_grain(hx, GRAIN["intensity"], GRAIN["saturation_mix"], 4)[0]
+            b = nodes[1].match_color(a, hr, 1.0, 1)[0]
+            c = nodes[2].apply_lut(b, os.path.basename(LUT_FILE), "auto", 10.0)[0]
+            return nodes[3].apply_unsharp(c, SHARPEN, False)[0]
+        stock_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            r = stock_step()
+            checksum += float(r[0, 0, 0, 0])
+        torch.cuda.synchronize(dev)
+        st_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 2)
+        stock = {"value": round(world * nS * H4K * W4K / 1e6 / (st_ms / 1e3), 1), "unit": "MP/s", "ms_per_step": round(st_ms, 2), "frames_per_gpu": nS,
+                 "api": "FastFilmGrain -> ColorMatchToReference -> VRGDG_LUTS -> FastUnsharpSharpen node classes, pageable host tensors in and out"}
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        alg_bytes = npix * 12                      # 6 B read + 6 B written per pixel (fp16 RGB), SURVEY 8(d)
-        achieved = alg_bytes / (ms_step / 1e3) / 1e9
-        traffic, prof = recorded_traffic()
+        alg = npix * 24                                       # 12 B read + 12 B written per fp32 pixel, SURVEY 8(d)
+        tr, st = recorded_traffic("headline_apply")
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": round(value, 1), "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "height": H, "width": W, "frame_dtype": "f16", "lut": os.path.basename(LUT_FILE),
-                       "distribution": "natural-like (4 octaves of upsampled noise + 2% white)", "parallelism": "frame-sharded dp%d" % world,
-                       "l2": "input (796 MB per GPU) and output are each larger than L2 (126 MB); no flush needed", "tile_path": tile_path},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": traffic, "kernel": "k_tile<half, grain|lut, unsharp>", "algorithmic_bytes_per_launch": alg_bytes,
-                         "peak_source": peak_src},
-            "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": frame_bytes,
-                    "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "api": "PostChain.run_host(pinned frames, chunk_frames=8)"},
+            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_4K, "height": H4K, "width": W4K, "frame_dtype": "f32", "lut": os.path.basename(LUT_FILE),
+                       "distribution": "natural-like (4 octaves of upsampled noise + 2% white), per-frame gain / offset",
+                       "parallelism": "frame-sharded dp%d; colour-match reference rows sharded, one 56-byte all-gather per step" % world,
+                       "collective": ("nccl all_gather inside every step" if world > 1 else "none at N=1 (single rank computes the whole reference frame)"),
+                       "ref_sums_identical_on_all_ranks": ref_sums_identical,
+                       "l2": "input (12.7 GB per GPU) and output are each far larger than L2 (126 MB); no flush needed", "tile_path": tile_path,
+                       "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
+            "roofline": dict(roofline(alg, ms_apply, {
+                "kernel": "k_tile<float, grain|colormatch|lut, unsharp> (the fused apply pass; dominant kernel of the step)",
+                "kernel_ms": round(ms_apply, 4), "kernel_share_of_step": round(ms_apply / ms_step, 3),
+                "frac_of_step": round(alg / (ms_step / 1e3) / 1e9 / peak, 4),
+                "moved_bytes_per_pixel": 36, "algorithmic_bytes_per_pixel": 24,
+                "limiter": "instruction issue (Philox + Box-Muller, nine fractional powers per pixel, LUT lerps), not HBM: see profiles/README.md",
+                "traffic": tr}), **(st or {})),
+            "step_breakdown_ms": {"moments_pass": round(ms_moments, 4), "apply_pass": round(ms_apply, 4),
+                                  "reference_allgather_and_host": round(max(ms_step - ms_moments - ms_apply, 0.0), 4)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
+                    "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "frames_per_gpu": nE,
+                    "api": "PostChain.run_host(pinned 4K fp32 frames, chunk_frames=%d), sub-batch of %d frames per GPU" % (chunk, nE),
+                    "achieved_gbs_each_way": round(e2e_bytes / (e2e_ms / 1e3) / 1e9, 2), "h2d_gbs": round(h2d, 1), "d2h_gbs": round(d2h, 1),
+                    "stock_nodes": stock},
+            "extra": extras,
             "gpu_launches": launches,
             "clocks": sampler.result(),
         }
         if world == 1 and not args.no_cpu:
-            mps, secs, threads = cpu_chain_sample(2, steps=2)
+            mps, secs, threads = cpu_full_chain(1, steps=2)
             line["cpu_baseline"] = {"value": round(mps, 3), "unit": "MP/s", "cores": threads, "kind": "port",
-                                    "sample": "2 x 1080p fp32 frames, best of 2, oracle port of FastFilmGrain -> VRGDG_LUTS -> FastUnsharpSharpen (%.1f s)" % secs}
+                                    "sample": "1 x 3840x2160 fp32 frame, best of 2, oracle port of FastFilmGrain -> ColorMatchToReference -> VRGDG_LUTS -> "
+                                              "FastUnsharpSharpen (%.1f s)" % secs}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -285,6 +438,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra lines and the stock-node leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -34,47 +34,96 @@ def result_device(images, numpy_path=False):
     return images.device
 
 
-def stream_frames(src, fn, chunk, out_device, device=None, out=None):
-    """Apply fn(cuda_frames, first_frame_index) -> cuda_frames over src [B,...] in chunks of `chunk` frames.
+_SIDE_STREAMS = {}
 
-    CUDA input: a single call (chunk ignored).  CPU input: chunks are uploaded on a side stream while the previous
-    chunk computes, results are downloaded on a third stream; pinned source/result tensors make those copies truly
-    asynchronous (result is pinned when the source is).  `out`: optional preallocated host result (reused across calls so
-    that pinning cost is paid once)."""
+
+def _side_streams(dev):
+    """(upload, download) streams of a device, created once (stream creation is not free and ComfyUI calls nodes repeatedly)."""
+    key = (dev.type, dev.index)
+    hit = _SIDE_STREAMS.get(key)
+    if hit is None:
+        hit = _SIDE_STREAMS[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return hit
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node).  Call BEFORE allocating /
+    first-touching pinned host buffers: a rank that stages frames through the other socket's memory pays the inter-socket
+    link on every PCIe transfer.  Returns the CPU list, or None when NVML / sched_setaffinity are unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
+def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
+    """Apply fn(cuda_frames, first_frame_index) -> cuda_frames over src [B,...] in chunks of `chunk` frames (0 / None = all).
+
+    CUDA input: chunked as well (the reference bounds device memory with its batch_size widget the same way, nodes.py:49-62);
+    one call when the chunk covers the batch.  CPU input: a three-stream pipeline - chunk k+1.. are uploaded into `depth`+1
+    reusable staging buffers while chunk k computes and earlier results download; only the last download is waited for.
+    Pinned source / result tensors make the copies truly asynchronous (the result is pinned when the source is).  `out`:
+    optional preallocated result on out_device (reused across calls so that pinning cost is paid once)."""
     B = int(src.shape[0])
     out_device = torch.device(out_device)
+    chunk = B if chunk is None or int(chunk) <= 0 else min(int(chunk), max(B, 1))
     if src.device.type == "cuda":
-        res = fn(src, 0)
-        return res if res.device == out_device else res.to(out_device)
+        if chunk >= B:
+            res = fn(src, 0)
+            return res if res.device == out_device else res.to(out_device)
+        res = torch.empty(src.shape, dtype=src.dtype, device=out_device)
+        for i in range(0, B, chunk):
+            res[i:i + chunk].copy_(fn(src[i:i + chunk], i))
+        return res
     dev = device if device is not None else compute_device()
     if B == 0:
         return torch.empty_like(src, device=out_device)
-    chunk = B if chunk is None or chunk <= 0 else int(chunk)
     src = src.contiguous()
     to_cpu = out_device.type == "cpu"
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream(dev)
-        up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        up, down = _side_streams(dev)
         if out is None:
             out = torch.empty(src.shape, dtype=src.dtype, pin_memory=src.is_pinned()) if to_cpu else torch.empty(src.shape, dtype=src.dtype, device=out_device)
         elif out.shape != src.shape or out.dtype != src.dtype or out.device != out_device:
             raise ValueError("vrgdg_b200: `out` must match the source frames in shape and dtype and live on %s" % out_device)
-        pending = None
-        for i in range(0, B, chunk):
+        n_chunks = (B + chunk - 1) // chunk
+        slots = [torch.empty((chunk,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev) for _ in range(min(n_chunks, max(1, int(depth)) + 1))]
+        for b in slots:
+            b.record_stream(up)
+        up.wait_stream(compute)                 # the staging buffers may recycle memory the compute stream is still using
+        slot_free = [None] * len(slots)         # event: the kernels that read this slot have finished
+        for ci, i in enumerate(range(0, B, chunk)):
+            s, n = ci % len(slots), min(chunk, B - i)
             with torch.cuda.stream(up):
-                d_in = src[i:i + chunk].to(dev, non_blocking=True)
+                if slot_free[s] is not None:
+                    up.wait_event(slot_free[s])
+                slots[s][:n].copy_(src[i:i + n], non_blocking=True)
                 ev_up = torch.cuda.Event()
                 ev_up.record(up)
             compute.wait_event(ev_up)
-            d_in.record_stream(compute)
-            d_out = fn(d_in, i)
+            d_out = fn(slots[s][:n], i)
             ev_done = torch.cuda.Event()
             ev_done.record(compute)
+            slot_free[s] = ev_done
             down.wait_event(ev_done)
             with torch.cuda.stream(down):
                 d_out.record_stream(down)
-                out[i:i + chunk].copy_(d_out, non_blocking=True)
-            pending = d_out
-        down.synchronize()
-        del pending
+                out[i:i + n].copy_(d_out, non_blocking=True)
+            del d_out
+        ev_last = torch.cuda.Event()
+        ev_last.record(down)
+        ev_last.synchronize()                   # the caller reads `out` on the host
+        compute.wait_stream(up)
     return out

@@ -26,6 +26,7 @@ class PostChain:
         self.grain, self.colormatch, self.lut, self.stencil, self.post_grain = grain, colormatch, lut, stencil, post_grain
         self._lut_dev = None
         self._ref_sums = None
+        self.timing = None          # set to a list to collect (moments_start, moments_end, apply_start, apply_end) CUDA events per call
         if lut is not None:
             self._lut_dev = ops.pack_lut(lut["lut_data"]["lut"], self.device)
         if colormatch is not None:
@@ -40,7 +41,7 @@ class PostChain:
         else:
             raise ValueError("colour match needs reference_image or ref_sums")
 
-    def _desc(self, frames, first_frame, keep):
+    def _desc(self, frames, first_frame, keep, ext_noise=None):
         d = nv.ChainDesc()
         if self.grain is not None:
             s = float(self.grain["saturation_mix"])
@@ -76,8 +77,13 @@ class PostChain:
         if self.colormatch is not None:
             # per-frame LAB moments of the colour-match INPUT (= grain output when grain is enabled): a first pass
             # that recomputes the counter-based grain instead of materialising it
-            sums = ops.chain_lab_moments(frames, d)
+            if self.timing is not None:
+                self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                self._ev[0].record()
+            sums = ops.chain_lab_moments(frames, d, ext_noise=ext_noise)
             params = ops.colormatch_params(sums, self._ref_sums)
+            if self.timing is not None:
+                self._ev[1].record()
             keep.append(params)
             t = float(self.colormatch.get("strength", 1.0))
             d.colormatch_enabled = 1
@@ -89,8 +95,20 @@ class PostChain:
         """frames: CUDA [B,H,W,3]; first_frame: absolute index of frames[0] in the clip (keys the grain).
         ext_noise (tests): N(0,1) tensor replacing the generator; fast_math then selects the production arithmetic."""
         keep = []
-        d = self._desc(frames, first_frame, keep)
-        return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out, fast_math=fast_math)
+        d = self._desc(frames, first_frame, keep, ext_noise)
+        if self.timing is None:
+            return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out, fast_math=fast_math)
+        ev = getattr(self, "_ev", None) if self.colormatch is not None else None
+        if ev is None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            ev[1].record()
+        ev[2].record()
+        res = ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out, fast_math=fast_math)
+        ev[3].record()
+        self.timing.append(tuple(ev))
+        self._ev = None
+        return res
 
     def run_host(self, frames_cpu, chunk_frames=8, first_frame=0, out=None):
         """Host frames in, host frames out: chunked upload / compute / download on three streams.  Pass pinned tensors

@@ -434,19 +434,32 @@ int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int W, int dt
   return chain_apply_impl(in, out, B, H, W, dtype, desc, ext_noise, (flags & VRGDG_CHAIN_FAST_MATH) != 0, stream);
 }
 
-int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, double* sums,
-                            void* scratch, int64_t scratch_bytes, void* stream) {
-  if (!desc) return fail(VRGDG_E_INVALID, "vrgdg_chain_lab_moments: null descriptor");
-  if (B < 0 || H <= 0 || W <= 0) return fail(VRGDG_E_INVALID, "vrgdg_chain_lab_moments: bad shape");
+static int chain_moments_impl(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, const void* ext_noise,
+                              double* sums, void* scratch, int64_t scratch_bytes, void* stream, const char* who) {
+  if (!desc) return fail(VRGDG_E_INVALID, "%s: null descriptor", who);
+  if (B < 0 || H <= 0 || W <= 0) return fail(VRGDG_E_INVALID, "%s: bad shape", who);
   PointParams P;
   zero_point(P, B, H, W);
   if (desc->grain_enabled) {
+    if (desc->grain_seed_mode != VRGDG_SEED_PER_CLIP && desc->grain_seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "%s: bad grain seed_mode %d", who, desc->grain_seed_mode);
     P.gI = desc->grain_intensity; P.gs = desc->grain_sat; P.goms = desc->grain_one_minus_sat;
     P.seed = desc->grain_seed; P.frame0 = desc->grain_frame0; P.seed_mode = desc->grain_seed_mode;
     grain_make_key(P.seed, P.seed_mode, P.gkey);
+    P.ext_noise = ext_noise;
   }
-  return moments_common(in, B, H, W, dtype, 0, H, desc->grain_enabled ? &P : nullptr, sums, scratch, scratch_bytes, stream,
-                        "vrgdg_chain_lab_moments");
+  return moments_common(in, B, H, W, dtype, 0, H, desc->grain_enabled ? &P : nullptr, sums, scratch, scratch_bytes, stream, who);
+}
+
+int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, double* sums,
+                            void* scratch, int64_t scratch_bytes, void* stream) {
+  return chain_moments_impl(in, B, H, W, dtype, desc, nullptr, sums, scratch, scratch_bytes, stream, "vrgdg_chain_lab_moments");
+}
+
+/* same with the grain stage reading the external N(0,1) tensor of vrgdg_chain_apply_ext (exact arithmetic), so that the statistics
+ * and the applied chain see the same grained frames */
+int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, const void* ext_noise,
+                                double* sums, void* scratch, int64_t scratch_bytes, void* stream) {
+  return chain_moments_impl(in, B, H, W, dtype, desc, ext_noise, sums, scratch, scratch_bytes, stream, "vrgdg_chain_lab_moments_ext");
 }
 
 int64_t vrgdg_adjust_scratch_bytes(int B, int H, int W, const vrgdg_adjust_desc* d) {

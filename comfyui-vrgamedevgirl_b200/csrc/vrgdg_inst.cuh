@@ -122,9 +122,18 @@ template <typename T>
 cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows, double* sums,
                            double* partials, const LaunchCtx& ctx) {
   if (P.B == 0) return cudaSuccess;
+  typedef typename Io<T>::word_t word_t;
+  constexpr int PX = (int)(sizeof(word_t) / sizeof(T));
+  const bool vec = (P.W % PX == 0) && ((reinterpret_cast<uintptr_t>(in) & (sizeof(word_t) - 1)) == 0);
   dim3 grid(MOMENT_BLOCKS, P.B);
-  if (grain) k_lab_moments<T, true><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), P, row0, rows, partials);
-  else k_lab_moments<T, false><<<grid, 256, 0, ctx.stream>>>(reinterpret_cast<const T*>(in), P, row0, rows, partials);
+  const T* src = reinterpret_cast<const T*>(in);
+  if (grain) {
+    if (vec) k_lab_moments<T, true, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+    else k_lab_moments<T, true, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+  } else {
+    if (vec) k_lab_moments<T, false, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+    else k_lab_moments<T, false, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

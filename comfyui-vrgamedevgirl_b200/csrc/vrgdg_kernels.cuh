@@ -77,14 +77,14 @@ struct PointParams {
 
 // One pixel through the enabled stages; (zr,zg,zb) = this pixel's N(0,1) triple (generator or external).
 template <int MASK, bool EXACT>
-__device__ __forceinline__ void process_pixel(const PointParams& P, const float* cmp, float zr, float zg, float zb,
+__device__ __forceinline__ void process_pixel(const PointParams& P, const CmFold& cmf, float zr, float zg, float zb,
                                               float& r, float& g, float& b) {
   if (MASK & ST_GRAIN) {
     if (EXACT) grain_blend_exact(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
     else grain_blend_fast(r, g, b, zr, zg, zb, P.gI, P.gs, P.goms);
   }
   if (MASK & ST_CM) {
-    colormatch_pixel(r, g, b, cmp, P.cm_t, P.cm_omt);
+    colormatch_fold_pixel(r, g, b, cmf);
   }
   if (MASK & ST_LUT) {
     float x0 = r, x1 = g, x2 = b;
@@ -99,9 +99,9 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const float*
 
 // two pixels at once: all per-pixel stages up to the LUT, then BOTH gathers issued before either is consumed
 template <int MASK, bool EXACT>
-__device__ __forceinline__ void process_pair(const PointParams& P, const float* cmp, const float* z, float* p) {
-  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[0], z[1], z[2], p[0], p[1], p[2]);
-  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmp, z[3], z[4], z[5], p[3], p[4], p[5]);
+__device__ __forceinline__ void process_pair(const PointParams& P, const CmFold& cmf, const float* z, float* p) {
+  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmf, z[0], z[1], z[2], p[0], p[1], p[2]);
+  process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmf, z[3], z[4], z[5], p[3], p[4], p[5]);
   if (MASK & ST_LUT) {
     float x[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
     lut3d_eval2<EXACT>(P.lut, p, p + 3);
@@ -135,7 +135,8 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
     if (pix0 >= P.hw) continue;
     const int64_t e0 = ((int64_t)frame * P.hw + pix0) * 3;
     const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
-    const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
+    CmFold cmf = {};                          // per-frame affine map of the colour match, folded with the strength (uniform per block)
+    if (MASK & ST_CM) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
     const uint32_t y = GRAIN ? (uint32_t)pix0 / (uint32_t)P.W : 0u;
     const uint32_t x = GRAIN ? (uint32_t)pix0 - y * (uint32_t)P.W : 0u;
 
@@ -180,7 +181,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
             grain_pair_normals(grain_pair_bits(P.gkey, gf, (x >> 1) + (uint32_t)(j >> 1), y), z);
           }
         }
-        process_pair<MASK, EXACT>(P, cmp, z, &v[3 * j]);
+        process_pair<MASK, EXACT>(P, cmf, z, &v[3 * j]);
       }
     } else {
       float zr = 0.f, zg = 0.f, zb = 0.f;
@@ -188,7 +189,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
         if (has_ext) { zr = nz[0]; zg = nz[1]; zb = nz[2]; }
         else grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
       }
-      process_pixel<MASK, EXACT>(P, cmp, zr, zg, zb, v[0], v[1], v[2]);
+      process_pixel<MASK, EXACT>(P, cmf, zr, zg, zb, v[0], v[1], v[2]);
     }
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
@@ -260,12 +261,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a lost TMA completion traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a lost TMA completion traps (reported as a CUDA error) instead of hanging the GPU.  The bound is WALL-CLOCK time
+// (20 s on %globaltimer, far beyond any preemption by time-slicing / MPS / a debugger on a shared box), the spin backs off with
+// nanosleep so that a long wait does not steal issue slots from the CTA that shares the SM.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t ns = 32;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+    if (globaltimer_ns() - t0 > 20000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
@@ -681,7 +695,8 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
       constexpr bool BGR = Io<T>::BGR;
       typedef typename Io<T>::noise_t noise_t;
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
-      const float* cmp = (MASK & ST_CM) ? (P.cm_params + (int64_t)frame * 12) : nullptr;
+      CmFold cmf = {};
+      if (MASK & ST_CM) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
       const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
       const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of TXE, TXE of 6)
@@ -727,7 +742,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
           // both pixels go through the stages unconditionally (their 2 x 3 LUT loads are then in flight together; a pixel
           // outside the image computes on staged zeros and is discarded) - the branchy form serialised the two gathers
           float p[6] = {e[BGR ? 2 : 0], e[1], e[BGR ? 0 : 2], e[BGR ? 5 : 3], e[4], e[BGR ? 3 : 5]};     // RGB for the stages
-          process_pair<MASK, EXACT>(P, cmp, z, p);
+          process_pair<MASK, EXACT>(P, cmf, z, p);
           if (in_a) { e[BGR ? 2 : 0] = p[0]; e[1] = p[1]; e[BGR ? 0 : 2] = p[2]; } else if (WORK) { e[0] = 0.f; e[1] = 0.f; e[2] = 0.f; }
           if (in_b) { e[BGR ? 5 : 3] = p[3]; e[4] = p[4]; e[BGR ? 3 : 5] = p[5]; } else if (WORK) { e[3] = 0.f; e[4] = 0.f; e[5] = 0.f; }
         }
@@ -789,36 +804,77 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <typename T, bool GRAIN>
+// u = (fy, fx - fy, fy - fz) of one pixel (Lab is an affine image of u, see cm_sums_to_lab_host)
+__device__ __forceinline__ void moments_add(float r, float g, float b, float* s1, float* s2) {
+  float fx, fy, fz;
+  rgb_to_fxyz(r, g, b, fx, fy, fz);
+  const float u1 = fx - fy, u2 = fy - fz;
+  s1[0] += fy; s1[1] += u1; s1[2] += u2;
+  s2[0] = fmaf(fy, fy, s2[0]); s2[1] = fmaf(u1, u1, s2[1]); s2[2] = fmaf(u2, u2, s2[2]);
+}
+
+// VEC: a thread moves 3 machine words = PX whole pixels per iteration (like k_point), one Philox call per pixel pair, the PX
+// pixels' sums are formed in fp32 (<= 8 terms) and then added to the thread's fp64 accumulators.  !VEC: one pixel per iteration.
+template <typename T, bool GRAIN, bool VEC>
 __global__ void __launch_bounds__(256)
 k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials) {
+  typedef typename Io<T>::word_t word_t;
+  typedef typename Io<T>::noise_t noise_t;
+  constexpr bool BGR = Io<T>::BGR;
+  constexpr int PX = VEC ? (int)(sizeof(word_t) / sizeof(T)) : 1;
+  constexpr int NE = PX * 3;
   const int frame = blockIdx.y;
   const int64_t pbeg = (int64_t)row0 * P.W, n = (int64_t)rows * P.W;
   const T* fbase = in + (int64_t)frame * P.hw * 3;
   const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
   const bool has_ext = GRAIN && (P.ext_noise != nullptr);
+  const CmFold nocm = {};
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    int64_t pif = pbeg + i;
-    const T* s = fbase + pif * 3;
-    float r = Elem<T>::ld(s[Io<T>::BGR ? 2 : 0]), g = Elem<T>::ld(s[1]), b = Elem<T>::ld(s[Io<T>::BGR ? 0 : 2]);
+  const int64_t groups = (n + PX - 1) / PX;      // VEC: n % PX == 0 (host-checked)
+  for (int64_t gi = (int64_t)blockIdx.x * 256 + threadIdx.x; gi < groups; gi += (int64_t)gridDim.x * 256) {
+    const int64_t pif = pbeg + gi * PX;
+    float v[NE], nz[NE];
+    union { word_t q[3]; T e[NE]; } u;
+    if (VEC) {
+      const word_t* src = reinterpret_cast<const word_t*>(fbase + pif * 3);
+      u.q[0] = __ldg(src); u.q[1] = __ldg(src + 1); u.q[2] = __ldg(src + 2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) u.e[i] = fbase[pif * 3 + i];
+    }
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 * j + c] = Elem<T>::ld(u.e[3 * j + (BGR ? 2 - c : c)]);
+    }
     if (GRAIN) {
-      float nr = 0.f, ng = 0.f, nb = 0.f;
+      const uint32_t y = (uint32_t)pif / (uint32_t)P.W, x = (uint32_t)pif - y * (uint32_t)P.W;
       if (has_ext) {
-        typedef typename Io<T>::noise_t noise_t;
         const noise_t* ns = reinterpret_cast<const noise_t*>(P.ext_noise) + ((int64_t)frame * P.hw + pif) * 3;
-        nr = noise_ld<noise_t>(ns[0]); ng = noise_ld<noise_t>(ns[1]); nb = noise_ld<noise_t>(ns[2]);
-        process_pixel<ST_GRAIN, true>(P, nullptr, nr, ng, nb, r, g, b);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) nz[i] = noise_ld<noise_t>(ns[i]);
+#pragma unroll
+        for (int j = 0; j < PX; ++j)
+          process_pixel<ST_GRAIN, true>(P, nocm, nz[3 * j], nz[3 * j + 1], nz[3 * j + 2], v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+      } else if (VEC) {
+#pragma unroll
+        for (int j = 0; j < PX; j += 2) {          // x is a multiple of PX (even): whole generator pairs
+          float z[6];
+          grain_pair_normals(grain_pair_bits(P.gkey, gf, (x >> 1) + (uint32_t)(j >> 1), y), z);
+          process_pixel<ST_GRAIN, false>(P, nocm, z[0], z[1], z[2], v[3 * j], v[3 * j + 1], v[3 * j + 2]);
+          process_pixel<ST_GRAIN, false>(P, nocm, z[3], z[4], z[5], v[3 * j + 3], v[3 * j + 4], v[3 * j + 5]);
+        }
       } else {
-        const uint32_t y = (uint32_t)pif / (uint32_t)P.W, x = (uint32_t)pif - y * (uint32_t)P.W;
-        grain_pixel_normals(P.gkey, gf, x, y, nr, ng, nb);
-        process_pixel<ST_GRAIN, false>(P, nullptr, nr, ng, nb, r, g, b);
+        float zr, zg, zb;
+        grain_pixel_normals(P.gkey, gf, x, y, zr, zg, zb);
+        process_pixel<ST_GRAIN, false>(P, nocm, zr, zg, zb, v[0], v[1], v[2]);
       }
     }
-    float L, A, Bv;
-    rgb_to_lab(r, g, b, L, A, Bv);
-    acc[0] += (double)L; acc[1] += (double)A; acc[2] += (double)Bv;
-    acc[3] += (double)L * (double)L; acc[4] += (double)A * (double)A; acc[5] += (double)Bv * (double)Bv;
+    float s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < PX; ++j) moments_add(v[3 * j], v[3 * j + 1], v[3 * j + 2], s1, s2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { acc[c] += (double)s1[c]; acc[3 + c] += (double)s2[c]; }
   }
   __shared__ double red[8][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -836,7 +892,8 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
   }
 }
 
-// sums[frame] = {n, S1[3], S2[3]}
+// sums[frame] = {n, S_L, S_a, S_b, S_LL, S_aa, S_bb}: fold of the block partials (sums over u = (fy, fx-fy, fy-fz)) in a fixed
+// order, then the affine change of variables u -> Lab in fp64 (cm_sums_to_lab_host)
 static __global__ void k_moments_final(const double* __restrict__ partials, int nb, double n, double* __restrict__ sums) {
   const int frame = blockIdx.x, lane = threadIdx.x;   // 32 threads
   double acc[6] = {0, 0, 0, 0, 0, 0};
@@ -849,12 +906,17 @@ static __global__ void k_moments_final(const double* __restrict__ partials, int 
   if (lane == 0) {
     double* o = sums + (int64_t)frame * 7;
     o[0] = n;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) o[1 + q] = acc[q];
+    o[1] = 116.0 * acc[0] - 16.0 * n;
+    o[2] = 500.0 * acc[1];
+    o[3] = 200.0 * acc[2];
+    o[4] = 13456.0 * acc[3] - 3712.0 * acc[0] + 256.0 * n;
+    o[5] = 250000.0 * acc[4];
+    o[6] = 40000.0 * acc[5];
   }
 }
 
-// params[b] = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]};  sd = sqrt(unbiased var) + 1e-5  (nodes.py:99-100,109-110)
+// params[b] = {k[3] = sd_ref/sd_img, c0[3] = mu_ref - mu_img*k, mu_img[3], sd_img[3]};  sd = sqrt(unbiased var) + 1e-5
+// (nodes.py:99-100,109-110); k and c0 are formed in fp64 and rounded once, so that matched = lab*k + c0 (one FMA)
 static __global__ void k_colormatch_params(const double* __restrict__ fs, int B, const double* __restrict__ rs, int n_ref,
                                     float* __restrict__ params) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -870,9 +932,10 @@ static __global__ void k_colormatch_params(const double* __restrict__ fs, int B,
     double nr = r[0], mr = r[1 + c] / nr;
     double varr = (r[4 + c] - r[1 + c] * mr) / (nr - 1.0);
     const float sdr = __fadd_rn((float)sqrt(varr > 0 ? varr : 0.0), 1e-5f);
-    p[c] = (float)m;
-    p[3 + c] = (float)((double)sdr / (double)sd);
-    p[6 + c] = (float)mr;
+    const double k = (double)sdr / (double)sd;
+    p[c] = (float)k;
+    p[3 + c] = (float)((double)(float)mr - (double)(float)m * k);               // the reference's means are fp32 tensors
+    p[6 + c] = (float)m;
     p[9 + c] = sd;
   }
 }

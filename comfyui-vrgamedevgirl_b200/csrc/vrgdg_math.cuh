@@ -41,7 +41,8 @@ VRGDG_HD float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 // a / D for the integer constants the exact kernels divide by (9, 25, 49, 81, 255): q = a*r, q' = fma(fma(-D, q, a), r, q) with
 // r = RN(1/D) is the correctly rounded quotient for every FINITE fp32 a (all finite bit patterns, subnormals included, compared
 // with __fdiv_rn on the GPU: tools/divconst_check.cu), 3 instructions instead of the ~9 of an IEEE division.  Outside that:
-// a = -0.0 gives +0.0 (equal value) and a = +-inf gives NaN (inf - inf in the residual); sums of frame values are finite.
+// a = -0.0 gives +0.0 (equal value); a = +-inf would give NaN (inf - inf in the residual), so a select returns q = a*r = +-inf
+// there, as IEEE division does (synthetic / HDR inputs can hold inf; NaN stays NaN either way).
 // Not valid for non-integer divisors (0.45 fails 0.7 % of inputs).
 template <int D>
 VRGDG_HD float div_const(float a) {
@@ -49,10 +50,12 @@ VRGDG_HD float div_const(float a) {
   const float r = 1.0f / (float)D;
 #if defined(__CUDA_ARCH__)
   const float q = __fmul_rn(a, r);
-  return __fmaf_rn(__fmaf_rn(-(float)D, q, a), r, q);
+  const float v = __fmaf_rn(__fmaf_rn(-(float)D, q, a), r, q);
+  return (fabsf(a) == INFINITY) ? q : v;
 #else
   const float q = mulx(a, r);
-  return fmaf(fmaf(-(float)D, q, a), r, q);
+  const float v = fmaf(fmaf(-(float)D, q, a), r, q);
+  return (fabsf(a) == INFINITY) ? q : v;
 #endif
 }
 
@@ -361,9 +364,15 @@ VRGDG_HD float lut_blend(float x, float y, float blend, float omb) {
 }
 
 // ---- sRGB <-> CIE Lab (kornia.color restatement; formulas in SURVEY.md §8c) ------------------------
-// The three fractional powers (x^2.4, x^(1/3), x^(1/2.4)) are evaluated as  seed = 2^(e*log2 x)  on the MUFU
-// (~1e-6 relative) followed by ONE Newton step of the matching integer root, which squares the error (result within
-// ~2 ulp of the correctly rounded value; torch.pow itself is ~1 ulp): ~12-16 instructions instead of ~60 for powf.
+// Colour match runs in "f-space": Lab is an affine image of (fx, fy, fz) = lab_f(XYZ / white),
+//   L = 116 fy - 16,  a = 500 (fx - fy),  b = 200 (fy - fz),
+// so the kernels never form L, a, b: the moments pass accumulates fy, fx - fy, fy - fz (cm_sums_to_lab turns their raw sums
+// into Lab sums in fp64), and the per-frame affine map  lab' = t (lab k + c0) + (1 - t) lab  is folded into three FMAs on
+// the f values (cm_fold).  Algebraically identical to nodes.py:105-115; the roundings differ at the 1e-7 level (the colour
+// match is tolerance-based: 1e-5 on RGB, kornia itself is unpinned).
+// Fractional powers: the INPUT side (x^2.4, x^(1/3)) is a MUFU seed 2^(e*log2 x) (~1e-6 relative) plus ONE Newton step of the
+// matching integer root (its error is amplified by sd_ref/sd_img and by the a/b differencing); the OUTPUT side x^(1/2.4) is the
+// MUFU seed alone (error <= ~5e-7 on a [0,1] value, not amplified).
 VRGDG_HD float approx_pow(float x, float e) {        // x > 0, relative error ~1e-6
 #if defined(__CUDA_ARCH__)
   float l, r;
@@ -401,7 +410,7 @@ VRGDG_HD float pow_2p4(float x) {
   float q = root5_pos(x);
   return (x * x) * (q * q);
 }
-// x^(1/2.4) = (x^(1/12))^5
+// x^(1/2.4), refined: (x^(1/12))^5 with one Newton step on the 12th root (kept for the accuracy tests; the kernels use the seed)
 VRGDG_HD float pow_inv2p4(float x) {
   float y = approx_pow(x, 0.083333336f);
   float y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y11 = (y8 * y2) * y;
@@ -410,28 +419,30 @@ VRGDG_HD float pow_inv2p4(float x) {
   return (y2 * y2) * y;
 }
 
-// Divisions by constants are multiplications by the rounded reciprocal (<= 1 ulp from the divided value); the colour-match
-// path is tolerance-based (1e-5 on RGB), not bit-pinned (kornia itself is unpinned), measured error vs the oracle ~7e-7.
+// Divisions by constants are multiplications by the rounded reciprocal (<= 1 ulp from the divided value).
 VRGDG_HD float srgb_to_linear(float c) {
   // where(c > 0.04045, ((c + 0.055) / 1.055) ** 2.4, c / 12.92)
-  return (c > 0.04045f) ? pow_2p4((c + 0.055f) * (float)(1.0 / 1.055)) : c * (float)(1.0 / 12.92);
+  return (c > 0.04045f) ? pow_2p4(fmaf(c, (float)(1.0 / 1.055), (float)(0.055 / 1.055))) : c * (float)(1.0 / 12.92);
 }
 VRGDG_HD float linear_to_srgb(float l) {
   // where(l > 0.0031308, 1.055 * clamp(l, min=thr) ** (1/2.4) - 0.055, 12.92 * l)
-  return (l > 0.0031308f) ? fmaf(1.055f, pow_inv2p4(fmaxf(l, 0.0031308f)), -0.055f) : 12.92f * l;
+  return (l > 0.0031308f) ? fmaf(1.055f, approx_pow(fmaxf(l, 0.0031308f), 0.41666666f), -0.055f) : 12.92f * l;
 }
 VRGDG_HD float lab_f(float t) {
   // where(t > 0.008856, clamp(t, min=0.008856) ** (1/3), 7.787 t + 4/29)
   return (t > 0.008856f) ? cbrt_pos(fmaxf(t, 0.008856f)) : fmaf(7.787f, t, (float)(4.0 / 29.0));
 }
+// rgb -> (fx, fy, fz): sRGB decode, OpenCV D65 matrix with the white point (0.95047, 1, 1.08883) folded into its rows, lab_f
+VRGDG_HD void rgb_to_fxyz(float r, float g, float b, float& fx, float& fy, float& fz) {
+  const float lr = srgb_to_linear(r), lg = srgb_to_linear(g), lb = srgb_to_linear(b);
+  const float x = fmaf((float)(0.180423 / 0.95047), lb, fmaf((float)(0.357580 / 0.95047), lg, (float)(0.412453 / 0.95047) * lr));
+  const float y = fmaf(0.072169f, lb, fmaf(0.715160f, lg, 0.212671f * lr));
+  const float z = fmaf((float)(0.950227 / 1.08883), lb, fmaf((float)(0.119193 / 1.08883), lg, (float)(0.019334 / 1.08883) * lr));
+  fx = lab_f(x); fy = lab_f(y); fz = lab_f(z);
+}
 VRGDG_HD void rgb_to_lab(float r, float g, float b, float& L, float& A, float& Bv) {
-  float lr = srgb_to_linear(r), lg = srgb_to_linear(g), lb = srgb_to_linear(b);
-  float x = fmaf(0.180423f, lb, fmaf(0.357580f, lg, 0.412453f * lr));
-  float y = fmaf(0.072169f, lb, fmaf(0.715160f, lg, 0.212671f * lr));
-  float z = fmaf(0.950227f, lb, fmaf(0.119193f, lg, 0.019334f * lr));
-  float fx = lab_f(x * (float)(1.0 / 0.95047));
-  float fy = lab_f(y);                                 // y / 1.0
-  float fz = lab_f(z * (float)(1.0 / 1.08883));
+  float fx, fy, fz;
+  rgb_to_fxyz(r, g, b, fx, fy, fz);
   L = fmaf(116.0f, fy, -16.0f);
   A = 500.0f * (fx - fy);
   Bv = 200.0f * (fy - fz);
@@ -440,32 +451,60 @@ VRGDG_HD float lab_finv(float f) {
   // where(f > 0.2068966, f ** 3, (f - 4/29) / 7.787)
   return (f > 0.2068966f) ? (f * f) * f : (f - (float)(4.0 / 29.0)) * (float)(1.0 / 7.787);
 }
-VRGDG_HD void lab_to_rgb(float L, float A, float Bv, float& r, float& g, float& b) {
-  float fy = (L + 16.0f) * (float)(1.0 / 116.0);
-  float fx = fmaf(A, (float)(1.0 / 500.0), fy);
-  float fz = fmaxf(fmaf(Bv, (float)(-1.0 / 200.0), fy), 0.0f);
-  float x = lab_finv(fx) * 0.95047f;
-  float y = lab_finv(fy);                              // * 1.0
-  float z = lab_finv(fz) * 1.08883f;
-  float lr = fmaf(-0.4985363261688878f, z, fmaf(-1.5371515162713185f, y, 3.2404813432005266f * x));
-  float lg = fmaf(0.0415559265582928f, z, fmaf(1.8759900014898907f, y, -0.9692549499965682f * x));
-  float lb = fmaf(1.0573110696453443f, z, fmaf(-0.2040413383665112f, y, 0.0556466391351772f * x));
+// (fx, fy, fz) -> rgb, clipped (kornia lab_to_rgb(clip=True) followed by nodes.py:121 clamp); fz >= 0 is the caller's job
+VRGDG_HD void fxyz_to_rgb(float fx, float fy, float fz, float& r, float& g, float& b) {
+  const float x = lab_finv(fx), y = lab_finv(fy), z = lab_finv(fz);       // XYZ / white; the white point is folded into the columns below
+  const float lr = fmaf((float)(-0.4985363261688878 * 1.08883), z, fmaf(-1.5371515162713185f, y, (float)(3.2404813432005266 * 0.95047) * x));
+  const float lg = fmaf((float)(0.0415559265582928 * 1.08883), z, fmaf(1.8759900014898907f, y, (float)(-0.9692549499965682 * 0.95047) * x));
+  const float lb = fmaf((float)(1.0573110696453443 * 1.08883), z, fmaf(-0.2040413383665112f, y, (float)(0.0556466391351772 * 0.95047) * x));
   r = clamp01(linear_to_srgb(lr));
   g = clamp01(linear_to_srgb(lg));
   b = clamp01(linear_to_srgb(lb));
 }
+VRGDG_HD void lab_to_rgb(float L, float A, float Bv, float& r, float& g, float& b) {
+  const float fy = (L + 16.0f) * (float)(1.0 / 116.0);
+  fxyz_to_rgb(fmaf(A, (float)(1.0 / 500.0), fy), fy, fmaxf(fmaf(Bv, (float)(-1.0 / 200.0), fy), 0.0f), r, g, b);
+}
 
 // nodes.py:112-115: matched = (lab - mu)/sd * sd_ref + mu_ref ; blended = t*matched + (1-t)*lab
-// p = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]}  (the ratio is formed once per frame in fp64)
+// p = {k[3] = sd_ref/sd_img, c0[3] = mu_ref - mu_img*k, mu_img[3], sd_img[3]}  (k and c0 are formed once per frame in fp64), so
+// matched = lab*k + c0 and blended = lab*(t*k + (1-t)) + t*c0.  In f-space:
+//   fy' = (L' + 16)/116 = fy*K_L + (t*c0_L - 16 K_L + 16)/116
+//   fx' = a'/500 + fy'  = (fx - fy)*K_a + t*c0_a/500 + fy'
+//   fz' = fy' - b'/200  = fy' - (fy - fz)*K_b - t*c0_b/200        (then max(fz', 0) as kornia does)
+struct CmFold { float ky, cy, ka, ca, kb, cb; };
+VRGDG_HD CmFold cm_fold(const float* p, float t, float omt) {
+  CmFold f;
+  f.ky = fmaf(t, p[0], omt);
+  f.ka = fmaf(t, p[1], omt);
+  f.kb = fmaf(t, p[2], omt);
+  f.cy = fmaf(-16.0f, f.ky, fmaf(t, p[3], 16.0f)) * (float)(1.0 / 116.0);
+  f.ca = (t * p[4]) * (float)(1.0 / 500.0);
+  f.cb = (t * p[5]) * (float)(1.0 / 200.0);
+  return f;
+}
+VRGDG_HD void colormatch_fold_pixel(float& r, float& g, float& b, const CmFold& f) {
+  float fx, fy, fz;
+  rgb_to_fxyz(r, g, b, fx, fy, fz);
+  const float fy2 = fmaf(fy, f.ky, f.cy);
+  const float fx2 = fmaf(fx - fy, f.ka, fy2 + f.ca);
+  const float fz2 = fmaxf(fmaf(fz - fy, f.kb, fy2 - f.cb), 0.0f);
+  fxyz_to_rgb(fx2, fy2, fz2, r, g, b);
+}
 VRGDG_HD void colormatch_pixel(float& r, float& g, float& b, const float* p, float t, float omt) {
-  float lab[3];
-  rgb_to_lab(r, g, b, lab[0], lab[1], lab[2]);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float m = fmaf(lab[c] - p[c], p[3 + c], p[6 + c]);
-    lab[c] = fmaf(t, m, omt * lab[c]);
-  }
-  lab_to_rgb(lab[0], lab[1], lab[2], r, g, b);
+  colormatch_fold_pixel(r, g, b, cm_fold(p, t, omt));
+}
+
+// Raw sums of the moments pass are over u = (fy, fx - fy, fy - fz): {n, S_u[3], S_uu[3]}.  Lab = (116 u0 - 16, 500 u1, 200 u2):
+//   S_L = 116 S_0 - 16 n ;  S_LL = 116^2 S_00 - 2*116*16 S_0 + 256 n ;  S_a = 500 S_1 ; S_aa = 500^2 S_11 ; S_b = 200 S_2 ; S_bb = 200^2 S_22
+inline void cm_sums_to_lab_host(const double* u, double* lab) {   // documentation of the fp64 fold in k_moments_final
+  lab[0] = u[0];
+  lab[1] = 116.0 * u[1] - 16.0 * u[0];
+  lab[2] = 500.0 * u[2];
+  lab[3] = 200.0 * u[3];
+  lab[4] = 13456.0 * u[4] - 3712.0 * u[1] + 256.0 * u[0];
+  lab[5] = 250000.0 * u[5];
+  lab[6] = 40000.0 * u[6];
 }
 
 // ---- 3x3 stencil epilogues: nodes.py:194-207, :278-287, :369-382 (numpy) and :171-174,:249-258,:345-349 (torch)

@@ -156,12 +156,22 @@ def colormatch_apply(images, params, t_strength, one_minus_t):
     return out
 
 
+def _check_out(out, t):
+    """A caller-supplied result tensor goes to the kernels as a raw pointer: it must be exactly what the wrappers would allocate."""
+    if not isinstance(out, torch.Tensor) or out.shape != t.shape or out.dtype != t.dtype or out.device != t.device or not out.is_contiguous():
+        raise ValueError("vrgdg_b200: `out` must be a contiguous tensor matching images in shape %s, dtype %s and device %s"
+                         % (tuple(t.shape), t.dtype, t.device))
+    nbytes = t.numel() * t.element_size()
+    if nbytes and out.data_ptr() < t.data_ptr() + nbytes and t.data_ptr() < out.data_ptr() + nbytes:
+        raise ValueError("vrgdg_b200: `out` must not overlap images (tile kernels read neighbouring pixels)")
+    return out
+
+
 def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=False):
     """Run the fused chain described by a ChainDesc.  `keepalive` holds tensors the descriptor points to."""
     t = _frames(images)
     B, H, W, _ = t.shape
-    if out is None:
-        out = torch.empty_like(t)
+    out = torch.empty_like(t) if out is None else _check_out(out, t)
     lib = nv.load_library()
     with torch.cuda.device(t.device):
         if ext_noise is not None:
@@ -174,16 +184,18 @@ def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=
     return out
 
 
-def chain_lab_moments(images, desc):
+def chain_lab_moments(images, desc, ext_noise=None):
+    """LAB sums [B,7] of stage 1 (grain) of `desc` applied to images; ext_noise: the N(0,1) tensor a chain_apply(ext_noise=...) will use."""
     t = _frames(images)
     B, H, W, _ = t.shape
     lib = nv.load_library()
     sums = torch.empty((B, 7), dtype=torch.float64, device=t.device)
     nbytes = int(lib.vrgdg_lab_moments_scratch_bytes(B))
     scratch = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=t.device)
+    n = _noise(ext_noise, t) if ext_noise is not None else None
     with torch.cuda.device(t.device):
-        nv.check(lib.vrgdg_chain_lab_moments(nv.ptr(t), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(sums), nv.ptr(scratch),
-                                             ctypes.c_int64(nbytes), nv.stream_ptr(t.device)))
+        nv.check(lib.vrgdg_chain_lab_moments_ext(nv.ptr(t), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(n), nv.ptr(sums),
+                                                 nv.ptr(scratch), ctypes.c_int64(nbytes), nv.stream_ptr(t.device)))
     return sums
 
 

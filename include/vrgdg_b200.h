@@ -125,7 +125,7 @@ VRGDG_API int vrgdg_stencil3x3(const void* in, void* out, int B, int H, int W, i
  * Step 1: per-frame raw LAB sums over image rows [row0,row0+rows): sums[b] = {n, S_L, S_a, S_b, S_LL, S_aa, S_bb}
  *         (7 doubles per frame; fixed-order two-level reduction, deterministic).  Row ranges exist so the
  *         reference image can be sharded by rows across ranks and merged by addition.
- * Step 2: params[b] = {mu_img[3], sd_ref/sd_img [3], mu_ref[3], sd_img[3]} fp32, sd = unbiased std + 1e-5 (:99-100,:109-110);
+ * Step 2: params[b] = {k[3] = sd_ref/sd_img, c0[3] = mu_ref - mu_img*k, mu_img[3], sd_img[3]} fp32, sd = unbiased std + 1e-5 (:99-100,:109-110);
  *         opaque to the caller, consumed by vrgdg_colormatch_apply / the chain.
  *         n_ref is 1 (broadcast) or B.
  * Step 3: out = clamp(lab_to_rgb(t*((lab-mu)/sd*sd_ref+mu_ref) + (1-t)*lab)). */
@@ -189,6 +189,11 @@ VRGDG_API int vrgdg_chain_apply_ext(const void* in, void* out, int B, int H, int
 VRGDG_API int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype,
                             const vrgdg_chain_desc* desc, double* sums,
                             void* scratch, int64_t scratch_bytes, void* stream);
+/* vrgdg_chain_lab_moments for a chain run with vrgdg_chain_apply_ext: the grain stage reads the same external N(0,1) tensor
+ * (null = the in-kernel generator), so the statistics describe exactly the frames the colour-match stage will see. */
+VRGDG_API int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, int dtype,
+                                const vrgdg_chain_desc* desc, const void* ext_noise, double* sums,
+                                void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- "adjust" pass of the Builder UI ---------------------------------------------------------------------------
  * Replaces _apply_adjust_tensor (VRGDG_LUTVideoTools.py:307-391): clamp, temperature/tint offset, exposure, contrast,

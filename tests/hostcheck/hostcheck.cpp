@@ -100,6 +100,20 @@ void hc_colormatch(const float* in, float* out, int64_t n, const float* params, 
   }
 }
 
+// LAB raw sums {n, S_L, S_a, S_b, S_LL, S_aa, S_bb} the way the moments kernel forms them: sums over u = (fy, fx-fy, fy-fz),
+// then the affine change of variables in double (cm_sums_to_lab_host)
+void hc_lab_sums(const float* in, int64_t n, double* sums7) {
+  double u[7] = {(double)n, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    float fx, fy, fz;
+    rgb_to_fxyz(in[3 * i], in[3 * i + 1], in[3 * i + 2], fx, fy, fz);
+    const float u1 = fx - fy, u2 = fy - fz;
+    u[1] += fy; u[2] += u1; u[3] += u2;
+    u[4] += (double)fy * fy; u[5] += (double)u1 * u1; u[6] += (double)u2 * u2;
+  }
+  cm_sums_to_lab_host(u, sums7);
+}
+
 // frames [H][W][3], border 0 replicate / 1 zero
 void hc_stencil(const float* in, float* out, int H, int W, int op, float s, int border, int exact) {
   for (int y = 0; y < H; ++y)

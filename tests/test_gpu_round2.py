@@ -1,0 +1,181 @@
+"""Round-2 GPU parity tests (through the C ABI):
+  * 64^3 / 65^3 LUTs (the common sizes of the reference's own files) bit-exact against outputs of the reference itself
+  * fp16 / bf16 frames against THE ORACLE run on the up-cast input (not against our own fp32 kernels): grain, unsharp, LUT and the
+    configs[1] chain in the benchmarked arithmetic (fast_math), at 1080p; tolerance 1 ulp of the 16-bit type
+  * the full configs[3] chain through PostChain on external noise (statistics and apply see the same grained frames)
+  * host-side contracts added this round (`out` validation, chunking of CUDA inputs)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import LUTS, load_golden, natural_frames, t, write_big_cube
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+ULP = {torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}      # spacing of the 16-bit type in [0.5, 1)
+
+
+def maxdiff(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+def _lut33(pkg):
+    return pkg.VRGDG_LUTS._parse_cube_file(os.path.join(LUTS, "B200 Vintage 33.cube"))
+
+
+# ------------------------------------------------------------------------------------------------------
+# LUT sizes 64 and 65
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [64, 65])
+def test_lut_64_65_bit_exact_vs_reference_outputs(pkg, cuda_device, tmp_path, size):
+    g = load_golden("lut_big")
+    data = pkg.VRGDG_LUTS._parse_cube_file(write_big_cube(str(tmp_path / ("big_%d.cube" % size)), size))
+    assert data["size"] == size
+    x, xn = t(g["x"]).to(cuda_device), t(g["xn"]).to(cuda_device)
+    before = pkg._native.launch_count()
+    out = pkg.VRGDG_LUTS._apply_cube_lut(x, data["lut"], data["domain_min"], data["domain_max"])
+    assert pkg._native.launch_count() > before
+    assert torch.equal(out.cpu(), t(g["s%d__s10" % size]))
+    lut_nodes = __import__("importlib").import_module(pkg.__name__ + ".lut_nodes")
+    assert torch.equal(lut_nodes._run_lut(t(g["x"]), data, 3.5), t(g["s%d__s3p5" % size]))            # strength blend, host tensor in / out
+    assert torch.equal(lut_nodes._run_lut(xn, data, 10.0).cpu(), t(g["s%d__nat" % size]))
+    o16 = lut_nodes._run_lut(t(g["x"]).half(), data, 10.0)
+    assert o16.dtype == torch.float16 and torch.equal(o16, t(g["s%d__fp16" % size]))                     # one rounding of identical fp32 values
+    # uint8 BGR frames through the same table == decode -> LUT -> encode of the oracle
+    # fused chain with the big table: fused == separate kernels (the cell table leaves L1 at this size: 25-26 MB)
+    nv = pkg._native
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=7), lut=dict(lut_data=data, strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    xf = natural_frames(2, 136, 248, seed=size, device=cuda_device)
+    a = pkg.ops.grain(xf, 0.04, 0.5, 0.5, seed=7, frame0=3)
+    b = pkg.ops.lut3d_apply(a, data["lut"].to(cuda_device), [0, 0, 0], [1, 1, 1], 1.0, 0.0)
+    c = pkg.ops.stencil3x3(b, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
+    assert maxdiff(chain(xf, first_frame=3), c) <= 2e-6
+
+
+def test_lut_65_full_size_vs_oracle(pkg, cuda_device, oracle, tmp_path):
+    """a whole 1080p frame through the 65^3 table (26 MB cell table, L2-resident gather) equals the oracle bit for bit"""
+    path = write_big_cube(str(tmp_path / "big_65.cube"), 65)
+    data = pkg.VRGDG_LUTS._parse_cube_file(path)
+    x = natural_frames(1, 1080, 1920, seed=65)
+    out = pkg.VRGDG_LUTS._apply_cube_lut(x.to(cuda_device), data["lut"], data["domain_min"], data["domain_max"]).cpu()
+    assert torch.equal(out, oracle.apply_lut(x, oracle.parse_cube(path), 10.0))
+
+
+# ------------------------------------------------------------------------------------------------------
+# 16-bit frames against the oracle on the up-cast input
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_half_precision_frames_vs_oracle_on_upcast_input_1080p(pkg, cuda_device, oracle, dt):
+    nv = pkg._native
+    x16 = natural_frames(1, 1080, 1920, seed=16).to(dt)
+    z16 = torch.randn(x16.shape, generator=torch.Generator().manual_seed(17)).to(dt)
+    x32, z32 = x16.float(), z16.float()
+    xd, zd = x16.to(cuda_device), z16.to(cuda_device)
+    lut = _lut33(pkg)
+    olut = oracle.parse_cube(os.path.join(LUTS, "B200 Vintage 33.cube"))
+    ulp = ULP[dt]
+
+    # grain on external noise: the kernel reproduces the fp32 op sequence, then rounds once
+    ref = oracle.film_grain(x32, 0.04, 0.5, 0, noise=z32)
+    got = pkg.ops.grain(xd, 0.04, 0.5, 0.5, seed=0, ext_noise=zd)
+    assert got.dtype == dt and torch.equal(got.cpu(), ref.to(dt))
+
+    # unsharp (NumPy-path semantics): fast arithmetic for 16-bit frames -> within one spacing of the rounded oracle
+    ref = oracle.unsharp_numpy(x32, 0.5)
+    got = pkg.ops.stencil3x3(xd, nv.STENCIL_BOX_UNSHARP, 0.5, nv.BORDER_REPLICATE)
+    assert got.dtype == dt and maxdiff(got.float(), ref) <= ulp
+
+    # LUT: exact fp32 lookup, one rounding
+    ref = oracle.apply_lut(x32, olut, 10.0)
+    got = pkg.ops.lut3d_apply(xd, lut["lut"].to(cuda_device), [0, 0, 0], [1, 1, 1], 1.0, 0.0)
+    assert torch.equal(got.cpu(), ref.to(dt))
+
+    # configs[1] chain, the arithmetic bench.py runs (FMA-contracted, fast stencil), on the reference's noise
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), lut=dict(lut_data=lut, strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5, border=nv.BORDER_REPLICATE), device=cuda_device)
+    ref = oracle.chain_grain_lut_unsharp(x32, z32, 0.04, 0.5, olut, 10.0, 0.5)
+    fast = chain(xd, ext_noise=zd, fast_math=True)
+    assert nv.last_tile_path() == "tma" and fast.dtype == dt
+    assert maxdiff(fast.float(), ref) <= ulp
+    exact = chain(xd, ext_noise=zd)
+    assert maxdiff(exact.float(), ref) <= ulp
+
+
+# ------------------------------------------------------------------------------------------------------
+# configs[3] chain through the public class, statistics and apply on the same external noise
+# ------------------------------------------------------------------------------------------------------
+def test_postchain_full_chain_on_reference_noise(pkg, cuda_device):
+    nv = pkg._native
+    g = load_golden("chain")
+    x, z = t(g["x"]).to(cuda_device), t(g["z"]).to(cuda_device)
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), colormatch=dict(reference_image=t(g["ref"]), strength=1.0),
+                                lut=dict(lut_data=_lut33(pkg), strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5, border=nv.BORDER_REPLICATE), device=cuda_device)
+    out = chain(x, ext_noise=z)
+    assert maxdiff(out, t(g["grain_cm_lut_unsharp"])) <= TOL
+    fast = chain(x, ext_noise=z, fast_math=True)                       # the arithmetic the benchmark runs
+    assert maxdiff(fast, t(g["grain_cm_lut_unsharp"])) <= TOL
+    # the moments pass honours the external noise: equal to moments of the materialised grained frames
+    grained = pkg.ops.grain(x, 0.04, 0.5, 0.5, seed=0, ext_noise=z)
+    d = nv.ChainDesc()
+    d.grain_enabled, d.grain_intensity, d.grain_sat, d.grain_one_minus_sat = 1, 0.04, 0.5, 0.5
+    assert torch.equal(pkg.ops.chain_lab_moments(x, d, ext_noise=z), pkg.ops.lab_moments(grained))
+
+
+def test_moments_vector_and_scalar_paths_agree(pkg, cuda_device, oracle):
+    """W % 4 == 0 takes the 48-byte vector path, odd widths the scalar one; both against the oracle, with and without grain"""
+    for W in (64, 61):
+        x = natural_frames(3, 40, W, seed=W)
+        sums = pkg.ops.lab_moments(x.to(cuda_device)).cpu()
+        ref = oracle.lab_moments_f64(x)
+        n = float(ref[0, 0])
+        assert torch.equal(sums[:, 0], ref[:, 0])
+        assert float((sums[:, 1:4] - ref[:, 1:4]).abs().max()) / n < 5e-5
+        assert torch.allclose(sums[:, 4:7], ref[:, 4:7], rtol=5e-6, atol=0.0)
+    # in-kernel grain: moments pass == moments of the frames the grain kernel writes (same generator, same arithmetic)
+    nv = pkg._native
+    for W, dt in ((64, torch.float32), (61, torch.float32), (64, torch.float16)):
+        x = natural_frames(2, 40, W, seed=3 * W, dtype=dt, device=cuda_device)
+        d = nv.ChainDesc()
+        d.grain_enabled, d.grain_intensity, d.grain_sat, d.grain_one_minus_sat, d.grain_seed, d.grain_frame0 = 1, 0.04, 0.5, 0.5, 42, 5
+        a = pkg.ops.chain_lab_moments(x, d)
+        b = pkg.ops.lab_moments(pkg.ops.grain(x.float(), 0.04, 0.5, 0.5, seed=42, frame0=5))
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-4), (W, dt)
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-side contracts
+# ------------------------------------------------------------------------------------------------------
+def test_chain_out_must_match_the_frames(pkg, cuda_device):
+    nv = pkg._native
+    x = natural_frames(2, 40, 64, seed=1, device=cuda_device)
+    chain = pkg.chain.PostChain(stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    good = torch.empty_like(x)
+    assert chain(x, out=good) is good
+    for bad in (torch.empty((1, 40, 64, 3), device=cuda_device), torch.empty_like(x, dtype=torch.float16), torch.empty(x.shape),
+                torch.empty((2, 40, 64, 6), device=cuda_device)[..., :3], x):
+        with pytest.raises(ValueError):
+            chain(x, out=bad)
+
+
+def test_stream_frames_chunks_cuda_inputs_too(pkg, cuda_device):
+    rt = __import__("importlib").import_module(pkg.__name__ + "._runtime")
+    x = natural_frames(5, 24, 32, seed=2, device=cuda_device)
+    calls = []
+
+    def fn(frames, first):
+        calls.append((int(frames.shape[0]), int(first)))
+        return frames * 0.5
+    out = rt.stream_frames(x, fn, 2, cuda_device)
+    assert calls == [(2, 0), (2, 2), (1, 4)] and torch.equal(out, x * 0.5)
+    calls.clear()
+    out = rt.stream_frames(x, fn, 0, torch.device("cpu"))
+    assert calls == [(5, 0)] and out.device.type == "cpu"
+    # host frames: more chunks than staging buffers, pinned and pageable sources
+    for src in (x.cpu(), x.cpu().pin_memory()):
+        calls.clear()
+        out = rt.stream_frames(src, fn, 1, torch.device("cpu"), cuda_device, depth=2)
+        assert [c[1] for c in calls] == [0, 1, 2, 3, 4] and torch.equal(out, src * 0.5)

@@ -133,13 +133,38 @@ def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
             var = (s[4:7] - s[1:4] * m) / (n - 1)
             return m.astype(np.float32), np.sqrt(var).astype(np.float32) + np.float32(1e-5)
         (mi, si), (mr, sr) = stats(fs), stats(ref_s)
-        params = np.concatenate([mi, (sr.astype(np.float64) / si.astype(np.float64)).astype(np.float32), mr, si]).astype(np.float32)
+        k = sr.astype(np.float64) / si.astype(np.float64)
+        params = np.concatenate([k.astype(np.float32), (mr.astype(np.float64) - mi.astype(np.float64) * k).astype(np.float32), mi, si]).astype(np.float32)
         xin = flat(c["x"][b])
         out = np.zeros_like(xin)
         hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 1.0, 0.0)
         assert np.abs(out - flat(c["out_t100"][b])).max() <= 1e-5
         hostcheck.hc_colormatch(P(xin), P(out), xin.shape[0], P(params), 0.6, 1.0 - 0.6)
         assert np.abs(out - flat(c["out_t60"][b])).max() <= 1e-5
+
+
+def test_fspace_moments_equal_lab_moments(hostcheck, oracle):
+    """the moments kernel sums (fy, fx-fy, fy-fz) and converts to Lab sums in fp64 (csrc/vrgdg_math.cuh::cm_sums_to_lab_host)"""
+    hostcheck.hc_lab_sums.argtypes = [vp, i64, vp]
+    c = load_golden("colormatch")
+    for b in range(2):
+        xin = flat(c["x"][b])
+        got = np.zeros(7, dtype=np.float64)
+        hostcheck.hc_lab_sums(P(xin), xin.shape[0], P(got))
+        ref = oracle.lab_moments_f64(t(c["x"][b:b + 1]))[0].numpy()
+        n = ref[0]
+        assert got[0] == n
+        assert np.abs(got[1:4] - ref[1:4]).max() / n < 5e-5
+        assert np.allclose(got[4:7], ref[4:7], rtol=5e-6, atol=0.0)
+
+
+def test_div_const_keeps_infinities(hostcheck):
+    hostcheck.hc_div_const.argtypes = [vp, vp, i64, ci]
+    x = np.array([np.inf, -np.inf, np.nan], dtype=np.float32)
+    o = np.empty_like(x)
+    for d in (9, 25, 49, 81, 255):
+        hostcheck.hc_div_const(P(x), P(o), 3, d)
+        assert o[0] == np.inf and o[1] == -np.inf and np.isnan(o[2])
 
 
 def test_div_const_is_the_correctly_rounded_quotient(hostcheck):
@@ -151,7 +176,7 @@ def test_div_const_is_the_correctly_rounded_quotient(hostcheck):
     bits = rng.integers(0, 2 ** 32, size=8_000_000, dtype=np.uint64).astype(np.uint32)
     special = np.array([0x00000000, 0x00000001, 0x007FFFFF, 0x00800000, 0x7F7FFFFF, 0xFF7FFFFF, 0x3F800000, 0x41100000, 0x80000001], dtype=np.uint32)
     x = np.concatenate([bits, special]).view(np.float32)
-    x = x[np.isfinite(x)]                                                   # finite inputs only: +-inf gives NaN (documented in div_const)
+    x = x[np.isfinite(x)]                                                   # +-inf / NaN: test_div_const_keeps_infinities
     o = np.empty_like(x)
     with np.errstate(all="ignore"):
         for d in (9, 25, 49, 81, 255):
