@@ -331,6 +331,21 @@ def run_b200(args):
             "value": round(world * n2 / 1e6 / (ms2 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms2, 4), "steps": ex_steps,
             "roofline": roofline(n2 * 12, ms2, dict({"kernel": "k_tile<half, grain|lut>", "traffic": tr2}, **(st2 or {})))}
         del x2, o2, c4
+        # configs[4]: temporal 3-frame sharpen, 512 x 1080p fp32 frames over 4 GPUs = 128 frames per GPU (labelled extension:
+        # the reference has no temporal operator); at N > 1 every step exchanges one halo frame per shard boundary (NCCL send/recv)
+        x5 = tile_frames(device_natural_frames(8, 1080, 1920, seed=100 + rank, dtype=torch.float32, dev=dev), 128)
+
+        def temporal_step():
+            prev, nxt = vdist.exchange_halo_frames(x5)
+            pkg.ops.temporal_sharpen(x5, SHARPEN, prev, nxt)
+        ms5, _ = timed(temporal_step, ex_steps, 3)
+        n5 = 128 * 1080 * 1920
+        extras["configs4_temporal_sharpen_1080p_f32"] = {
+            "workload": "configs[4] per-GPU shard: temporal 3-frame unsharp, 128 x 1920x1080 fp32 frames per GPU, one halo frame per shard boundary "
+                        "(extension without a reference counterpart; parity unpinned)",
+            "value": round(world * n5 / 1e6 / (ms5 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms5, 4), "steps": ex_steps,
+            "roofline": roofline(n5 * 24, ms5, {"kernel": "k_temporal3<float>"})}
+        del x5
 
     # ---- end to end through the public API: pinned host frames -> pinned host frames (sub-batch) ----
     nE = min(E2E_FRAMES, FRAMES_4K)

@@ -14,6 +14,7 @@ from .filter_nodes import (  # noqa: F401
     FastUnsharpSharpen,
 )
 from .lut_nodes import VRGDG_LUTS, VRGDG_MakeLUT  # noqa: F401
+from . import chain_nodes as _chain_nodes
 
 __version__ = "0.1.0"
 
@@ -37,5 +38,10 @@ NODE_DISPLAY_NAME_MAPPINGS = {
     "VRGDG_LUTS": "VRGDG_LUTS",
     "VRGDG_MakeLUT": "VRGDG_MakeLUT",
 }
+
+# graph-reachable entries to the fused kernels and the video-enhance tensor path: two reference keys
+# (VRGDG_VideoEnhanceNodes.py:422-437, VRGDG_StandaloneVideoEnhancerNodes.py:897-903) and two extra keys of this package
+NODE_CLASS_MAPPINGS.update(_chain_nodes.NODE_CLASS_MAPPINGS)
+NODE_DISPLAY_NAME_MAPPINGS.update(_chain_nodes.NODE_DISPLAY_NAME_MAPPINGS)
 
 __all__ = ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS"]

@@ -6,6 +6,7 @@
 #include "vrgdg_adjust.cuh"
 #include "vrgdg_resize.cuh"
 #include "vrgdg_lanczos.cuh"
+#include "vrgdg_temporal.cuh"
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
@@ -545,6 +546,26 @@ int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, f
   cudaError_t e = (dtype == VRGDG_F32) ? BL(float) : ((dtype == VRGDG_F16) ? BL(__half) : BL(__nv_bfloat16));
 #undef BL
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_blend");
+  return VRGDG_OK;
+}
+
+int vrgdg_temporal_sharpen(const void* in, void* out, int B, int H, int W, int dtype, float strength, const void* prev_frame,
+                           const void* next_frame, void* stream) {
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_temporal_sharpen");
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  const size_t es = elem_size(dtype);
+  if ((prev_frame && reinterpret_cast<uintptr_t>(prev_frame) % es) || (next_frame && reinterpret_cast<uintptr_t>(next_frame) % es))
+    return fail(VRGDG_E_ALIGN, "vrgdg_temporal_sharpen: halo frame pointer not aligned to its element size");
+  if (in == out) return fail(VRGDG_E_INVALID, "vrgdg_temporal_sharpen cannot run in place (a frame is read again as its successor's neighbour)");
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  TemporalParams P;
+  P.B = B; P.frame_elems = (int64_t)H * W * 3; P.strength = strength; P.prev = prev_frame; P.next = next_frame;
+#define TS(T) launch_temporal<T>(in, out, P, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, TS);
+#undef TS
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_temporal_sharpen");
   return VRGDG_OK;
 }
 

@@ -4,7 +4,9 @@
 #include <algorithm>
 #include "vrgdg_adjust.cuh"
 #include "vrgdg_resize.cuh"
+#include "vrgdg_temporal.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace vrgdg {
 
@@ -168,6 +170,7 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_adjust<T>(const void*, void*, const AdjustParams&, int, float*, float*, const LaunchCtx&);              \
   template cudaError_t launch_resize<T>(const void*, void*, const ResizeParams&, const LaunchCtx&);                       \
   template cudaError_t launch_blend<T>(const void*, const void*, void*, int64_t, float, float, const LaunchCtx&);         \
+  template cudaError_t launch_temporal<T>(const void*, void*, const TemporalParams&, const LaunchCtx&);                   \
   template void tile_geometry<T>(int, int, int&, int&, int&, int&);
 
 #define VRGDG_INSTANTIATE_CODECS(T)                                                                                       \

@@ -420,17 +420,26 @@ VRGDG_HD float pow_inv2p4(float x) {
 }
 
 // Divisions by constants are multiplications by the rounded reciprocal (<= 1 ulp from the divided value).
+// Both sides of each where() are evaluated (the power on an argument clamped into its own domain) and the result is SELECTED:
+// written as a ternary around the power the compiler emits a divergent branch per channel (BSSY / BRA / BSYNC: 4 extra
+// instructions per conditional and two passes for every warp that holds one dark pixel).
 VRGDG_HD float srgb_to_linear(float c) {
   // where(c > 0.04045, ((c + 0.055) / 1.055) ** 2.4, c / 12.92)
-  return (c > 0.04045f) ? pow_2p4(fmaf(c, (float)(1.0 / 1.055), (float)(0.055 / 1.055))) : c * (float)(1.0 / 12.92);
+  const float p = pow_2p4(fmaf(fmaxf(c, 0.04045f), (float)(1.0 / 1.055), (float)(0.055 / 1.055)));
+  const float l = c * (float)(1.0 / 12.92);
+  return (c > 0.04045f) ? p : l;
 }
 VRGDG_HD float linear_to_srgb(float l) {
   // where(l > 0.0031308, 1.055 * clamp(l, min=thr) ** (1/2.4) - 0.055, 12.92 * l)
-  return (l > 0.0031308f) ? fmaf(1.055f, approx_pow(fmaxf(l, 0.0031308f), 0.41666666f), -0.055f) : 12.92f * l;
+  const float p = fmaf(1.055f, approx_pow(fmaxf(l, 0.0031308f), 0.41666666f), -0.055f);
+  const float q = 12.92f * l;
+  return (l > 0.0031308f) ? p : q;
 }
 VRGDG_HD float lab_f(float t) {
   // where(t > 0.008856, clamp(t, min=0.008856) ** (1/3), 7.787 t + 4/29)
-  return (t > 0.008856f) ? cbrt_pos(fmaxf(t, 0.008856f)) : fmaf(7.787f, t, (float)(4.0 / 29.0));
+  const float p = cbrt_pos(fmaxf(t, 0.008856f));
+  const float q = fmaf(7.787f, t, (float)(4.0 / 29.0));
+  return (t > 0.008856f) ? p : q;
 }
 // rgb -> (fx, fy, fz): sRGB decode, OpenCV D65 matrix with the white point (0.95047, 1, 1.08883) folded into its rows, lab_f
 VRGDG_HD void rgb_to_fxyz(float r, float g, float b, float& fx, float& fy, float& fz) {

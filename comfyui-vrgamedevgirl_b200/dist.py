@@ -43,3 +43,25 @@ def reference_sums_distributed(reference_image, moments_fn=None, group=None):
     for part in gathered:            # fixed rank order -> identical on every rank
         total += part
     return total
+
+
+def exchange_halo_frames(frames, group=None):
+    """(prev, next) = the last frame of the previous rank and the first frame of the next rank ([H,W,3] each, None at the clip's
+    ends) for the temporal 3-frame stencil (configs[4], an extension without a reference counterpart): one frame sent to each
+    neighbour, point to point.  Without a process group: (None, None)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, None
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1 or frames.shape[0] == 0:
+        return None, None
+    first, last = frames[0].contiguous(), frames[-1].contiguous()
+    prev = torch.empty_like(first) if rank > 0 else None
+    nxt = torch.empty_like(first) if rank + 1 < world else None
+    ops_ = []
+    if rank > 0:
+        ops_ += [dist.P2POp(dist.isend, first, rank - 1, group), dist.P2POp(dist.irecv, prev, rank - 1, group)]
+    if rank + 1 < world:
+        ops_ += [dist.P2POp(dist.isend, last, rank + 1, group), dist.P2POp(dist.irecv, nxt, rank + 1, group)]
+    for req in dist.batch_isend_irecv(ops_):
+        req.wait()
+    return prev, nxt

@@ -256,6 +256,28 @@ def blend(a, b, weight_a, weight_b):
     return out
 
 
+def temporal_sharpen(images, strength, prev_frame=None, next_frame=None):
+    """3-frame temporal unsharp over a clip [T,H,W,3] (configs[4]; labelled extension, see vrgdg_temporal_sharpen).  prev_frame /
+    next_frame: [H,W,3] (or [1,H,W,3]) neighbours of the first / last frame when the clip is a shard of a longer one."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+
+    def halo(h, name):
+        if h is None:
+            return None
+        h = nv.require_cuda(h, name)
+        if h.numel() != H * W * 3 or h.dtype != t.dtype or h.device != t.device:
+            raise ValueError("vrgdg_b200: %s must be one frame [%d,%d,3] of dtype %s on %s" % (name, H, W, t.dtype, t.device))
+        return h
+    p, n = halo(prev_frame, "prev_frame"), halo(next_frame, "next_frame")
+    out = torch.empty_like(t)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_temporal_sharpen(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], _f32(strength), nv.ptr(p), nv.ptr(n),
+                                            nv.stream_ptr(t.device)))
+    return out
+
+
 _LANCZOS_TABLES = {}
 
 

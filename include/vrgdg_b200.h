@@ -236,6 +236,15 @@ VRGDG_API int vrgdg_resize(const void* in, void* out, int B, int Hs, int Ws, int
 VRGDG_API int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, float weight_a, float weight_b,
                 void* stream);
 
+/* ---- temporal 3-frame unsharp (BASELINE.json configs[4]) — LABELLED EXTENSION, no reference counterpart --------------------
+ * The reference has no temporal operator (VRGDG_VideoEnhanceNodes.py holds no sharpen / blur / stencil), so the
+ * specification is this library's:  out[t] = clamp(x[t] + s * (x[t] - (x[t-1] + x[t] + x[t+1]) / 3), 0, 1), fp32, one rounding
+ * per operation in that order, frames outside the clip replicated.  prev_frame / next_frame: the frame before in[0] / after
+ * in[B-1] when the clip is sharded across calls or ranks (device pointers, one frame each, frame dtype), or null at the clip's
+ * ends.  Must not run in place. */
+VRGDG_API int vrgdg_temporal_sharpen(const void* in, void* out, int B, int H, int W, int dtype, float strength,
+                           const void* prev_frame, const void* next_frame, void* stream);
+
 /* ---- Lanczos4 resize of uint8 frames -----------------------------------------------------------------
  * _resize_frames (VRGDG_StandaloneVideoEnhancerNodes.py:213-230) = cv2.resize(frame, (w, h), interpolation=cv2.INTER_LANCZOS4)
  * on uint8 HWC frames; bit-identical to OpenCV 4.x (fixed-point 8-tap tables, border replication).

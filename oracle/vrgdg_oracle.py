@@ -560,6 +560,20 @@ def chain_full(images, noise, grain_intensity, saturation_mix, reference_image, 
     return unsharp_numpy(x, sharpen_strength)
 
 
+def temporal_sharpen(frames, strength, prev_frame=None, next_frame=None):
+    """configs[4] temporal 3-frame unsharp.  NOT a restatement of reference code: the reference has no temporal operator,
+    so this NumPy function IS the specification (parity unpinned):
+        out[t] = clip(x[t] + s * (x[t] - (x[t-1] + x[t] + x[t+1]) / 3), 0, 1), fp32, frames outside the clip replicated."""
+    x = frames.detach().cpu().float().numpy()
+    first = x[:1] if prev_frame is None else prev_frame.detach().cpu().float().numpy().reshape(x[:1].shape)
+    last = x[-1:] if next_frame is None else next_frame.detach().cpu().float().numpy().reshape(x[:1].shape)
+    prev = np.concatenate([first, x[:-1]], axis=0)
+    nxt = np.concatenate([x[1:], last], axis=0)
+    mean = ((prev + x) + nxt) / np.float32(3.0)
+    out = x + np.float32(strength) * (x - mean)
+    return torch.from_numpy(np.clip(out, 0.0, 1.0).astype(np.float32))
+
+
 def lab_reference_f64(rgb):
     """Independent float64 CIE evaluation (numpy, textbook formulas) used only to sanity-check rgb_to_lab."""
     c = np.asarray(rgb, dtype=np.float64)

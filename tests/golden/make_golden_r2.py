@@ -52,6 +52,46 @@ def main():
     arrays = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in out.items()}
     np.savez_compressed(os.path.join(HERE, "lut_big.npz"), **arrays)
     print("lut_big", {k: tuple(v.shape) for k, v in arrays.items()})
+    restore_node_and_api()
+
+
+def restore_node_and_api():
+    """the two reference node classes of the "next" rows: API dump + outputs of VRGDGVideoEnhanceRestoreOriginal.restore"""
+    import json
+    import torch.nn.functional as F
+    ns = {"torch": torch, "F": F, "VIDEO_ENHANCE_CONTEXT": "VRGDG_VIDEO_ENHANCE_CONTEXT", "_log": lambda *a, **k: None}
+    RH._extract(os.path.join(RH.REFERENCE_ROOT, "VRGDG_VideoEnhanceNodes.py"),
+                {"_interpolation", "_resize_batch", "_restore_batch", "VRGDGVideoEnhanceRestoreOriginal"}, ns)
+    ns2 = {}
+    RH._extract(os.path.join(RH.REFERENCE_ROOT, "VRGDG_StandaloneVideoEnhancerNodes.py"), {"VRGDGStandaloneVideoEnhancer"}, ns2)
+    api = {}
+    for key, cls in (("VRGDGVideoEnhanceRestoreOriginal", ns["VRGDGVideoEnhanceRestoreOriginal"]), ("VRGDGStandaloneVideoEnhancer", ns2["VRGDGStandaloneVideoEnhancer"])):
+        api[key] = {"INPUT_TYPES": json.loads(json.dumps(cls.INPUT_TYPES())), "RETURN_TYPES": list(cls.RETURN_TYPES), "FUNCTION": cls.FUNCTION,
+                    "CATEGORY": cls.CATEGORY, "RETURN_NAMES": list(getattr(cls, "RETURN_NAMES", ())), "DESCRIPTION": getattr(cls, "DESCRIPTION", None),
+                    "OUTPUT_NODE": bool(getattr(cls, "OUTPUT_NODE", False))}
+    display = {"VRGDGVideoEnhanceRestoreOriginal": "Video Enhance - Restore Original Resolution", "VRGDGStandaloneVideoEnhancer": "VRGDG Standalone Video Enhancer"}
+    for key, name in display.items():      # check against the reference's own mapping text
+        src = open(os.path.join(RH.REFERENCE_ROOT, "VRGDG_VideoEnhanceNodes.py" if "Restore" in key else "VRGDG_StandaloneVideoEnhancerNodes.py"), encoding="utf-8").read()
+        assert '"%s": "%s"' % (key, name) in src, key
+    with open(os.path.join(HERE, "reference_meta_r2.json"), "w", encoding="utf-8") as fh:
+        json.dump({"api": api, "display_names": display}, fh, indent=1, ensure_ascii=True)
+    node = ns["VRGDGVideoEnhanceRestoreOriginal"]()
+    originals = natural_frames(5, 30, 40, seed=41)
+    ltx = natural_frames(4, 24, 32, seed=42)
+    out = {"originals": originals, "ltx": ltx}
+    cases = []
+    for ci, (fit, method, strength) in enumerate((("Stretch to dimensions", "Bicubic (recommended)", 1.0), ("Stretch to dimensions", "Bilinear", 0.4),
+                                                  ("Fit with letterbox (preserve all)", "Area", 0.75), ("Crop to fill", "Nearest", 1.0))):
+        ctx = {"original_frames": originals, "source_height": 30, "source_width": 40, "frame_count": 5, "fit_mode": fit, "fps": 24.0}
+        res = node.restore(ltx, ctx, method, strength)
+        out["case%d" % ci] = res[0]
+        assert res[1:] == (5, 40, 30, 24.0)
+        cases.append([fit, method, strength])
+    arrays = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    np.savez_compressed(os.path.join(HERE, "restore_node.npz"), **arrays)
+    with open(os.path.join(HERE, "restore_node_cases.json"), "w", encoding="utf-8") as fh:
+        json.dump(cases, fh)
+    print("restore_node", {k: tuple(v.shape) for k, v in arrays.items()})
 
 
 if __name__ == "__main__":

@@ -179,3 +179,106 @@ def test_stream_frames_chunks_cuda_inputs_too(pkg, cuda_device):
         calls.clear()
         out = rt.stream_frames(src, fn, 1, torch.device("cpu"), cuda_device, depth=2)
         assert [c[1] for c in calls] == [0, 1, 2, 3, 4] and torch.equal(out, src * 0.5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# graph-reachable nodes added this round
+# ------------------------------------------------------------------------------------------------------
+def test_postchain_node_equals_the_four_stock_nodes(pkg, cuda_device, oracle):
+    node = pkg.NODE_CLASS_MAPPINGS["VRGDG_B200_PostChain"]()
+    x = natural_frames(3, 72, 96, seed=8)
+    ref_img = natural_frames(1, 50, 60, seed=9) * 0.8
+    # without grain the node is deterministic: compare with the oracle composition colour match -> LUT -> unsharp
+    out = node.apply_chain(x, 0.0, 0.5, 0.7, "B200 Vintage 33.cube", 6.0, "unsharp", 0.5, False, 2, reference_image=ref_img)[0]
+    want = oracle.unsharp_numpy(oracle.apply_lut(oracle.color_match(x, ref_img, 0.7, 1), oracle.parse_cube(os.path.join(LUTS, "B200 Vintage 33.cube")), 6.0), 0.5)
+    assert out.device.type == "cpu" and maxdiff(out, want) <= TOL
+    # and the same as the stock node classes applied one after the other
+    b = pkg.ColorMatchToReference().match_color(x, ref_img, 0.7, 1)[0]
+    c = pkg.VRGDG_LUTS().apply_lut(b, "B200 Vintage 33.cube", "auto", 6.0)[0]
+    d = pkg.FastUnsharpSharpen().apply_unsharp(c, 0.5, False)[0]
+    assert maxdiff(out, d) <= 2e-6
+    # with grain: reproducible under torch.manual_seed like FastFilmGrain, independent of the upload chunking
+    torch.manual_seed(5)
+    g1 = node.apply_chain(x, 0.04, 0.5, 1.0, "none", 10.0, "laplacian", 0.3, True, 1)[0]
+    torch.manual_seed(5)
+    g2 = node.apply_chain(x, 0.04, 0.5, 1.0, "none", 10.0, "laplacian", 0.3, True, 0)[0]
+    assert torch.equal(g1, g2) and not torch.equal(g1, x)
+    # nothing enabled -> the input itself
+    assert node.apply_chain(x, 0.0, 0.5, 1.0, "none", 10.0, "none", 0.5, False, 8)[0] is x
+
+
+def test_enhance_frames_node_equals_effects_batch(pkg, cuda_device):
+    g = load_golden("effects")
+    vt = __import__("importlib").import_module(pkg.__name__ + ".video_tools")
+    node = pkg.NODE_CLASS_MAPPINGS["VRGDG_B200_EnhanceFrames"]()
+    xe = t(g["xe"])
+    out = node.enhance(xe, 0.8, 0.04, 0.5, 42, 7, True)[0]
+    want = vt._apply_effects_batch(xe, {"sharpen_enabled": True, "sharpen_strength": 0.8, "grain_enabled": True, "grain_intensity": 0.04,
+                                        "saturation_mix": 0.5, "seed": 42, "use_gpu": True}, 7)
+    assert torch.equal(out, want)
+    assert torch.equal(node.enhance(xe, 0.8, 0.0, 0.5, 42, 7, False)[0], t(g["sharp_only"]))        # the reference's unsharp output (use_gpu False)
+    assert torch.equal(node.enhance(xe, 0.8, 0.04, 0.5, 42, 7, False)[0], vt._apply_effects_batch(xe, {"sharpen_enabled": True, "sharpen_strength": 0.8,
+                       "grain_enabled": True, "grain_intensity": 0.04, "saturation_mix": 0.5, "seed": 42, "use_gpu": False}, 7))
+
+
+def test_restore_original_node_vs_reference_outputs(pkg, cuda_device):
+    import json
+    from helpers import GOLDEN
+    g = load_golden("restore_node")
+    with open(os.path.join(GOLDEN, "restore_node_cases.json")) as fh:
+        cases = json.load(fh)
+    node = pkg.NODE_CLASS_MAPPINGS["VRGDGVideoEnhanceRestoreOriginal"]()
+    for ci, (fit, method, strength) in enumerate(cases):
+        ctx = {"original_frames": t(g["originals"]), "source_height": 30, "source_width": 40, "frame_count": 5, "fit_mode": fit, "fps": 24.0}
+        frames, n, w, h, fps = node.restore(t(g["ltx"]), ctx, method, strength)
+        assert (n, w, h, fps) == (5, 40, 30, 24.0) and frames.device.type == "cpu"
+        tol = 0.0 if method in ("Nearest", "Area") else 2e-6                      # bilinear / bicubic: ATen's own kernels differ by that much
+        assert maxdiff(frames, t(g["case%d" % ci])) <= tol, (fit, method)
+    with pytest.raises(ValueError):
+        node.restore(t(g["ltx"])[:1], dict(ctx, frame_count=20), "Bilinear", 1.0)
+    assert pkg.NODE_CLASS_MAPPINGS["VRGDGStandaloneVideoEnhancer"]().return_output(None) == ("",)
+
+
+# ------------------------------------------------------------------------------------------------------
+# configs[4]: temporal 3-frame sharpen — a labelled extension (no reference operator exists; the NumPy oracle IS the specification)
+# ------------------------------------------------------------------------------------------------------
+def test_temporal_sharpen_vs_spec_oracle(pkg, cuda_device, oracle):
+    x = natural_frames(6, 37, 53, seed=70)                       # odd sizes: scalar path
+    x[3] = natural_frames(1, 37, 53, seed=71)[0]                 # a scene cut
+    got = pkg.ops.temporal_sharpen(x.to(cuda_device), 0.7)
+    assert torch.equal(got.cpu(), oracle.temporal_sharpen(x, 0.7))
+    xv = natural_frames(5, 40, 64, seed=72)                      # vector path
+    want = oracle.temporal_sharpen(xv, 1.3)
+    assert torch.equal(pkg.ops.temporal_sharpen(xv.to(cuda_device), 1.3).cpu(), want)
+    # a single frame and an empty clip
+    assert torch.equal(pkg.ops.temporal_sharpen(xv[:1].to(cuda_device), 1.3).cpu(), oracle.temporal_sharpen(xv[:1], 1.3))
+    assert pkg.ops.temporal_sharpen(xv[:0].to(cuda_device), 1.3).shape == (0, 40, 64, 3)
+    # shards with halo frames == the whole clip (frame-sharded ranks exchange one frame per boundary, dist.exchange_halo_frames)
+    d = xv.to(cuda_device)
+    a = pkg.ops.temporal_sharpen(d[:2], 1.3, None, d[2])
+    b = pkg.ops.temporal_sharpen(d[2:], 1.3, d[1], None)
+    assert torch.equal(torch.cat([a, b]).cpu(), want)
+    # 16-bit frames: fp32 arithmetic on the up-cast input, one rounding
+    for dt in (torch.float16, torch.bfloat16):
+        xh = xv.to(dt)
+        assert torch.equal(pkg.ops.temporal_sharpen(xh.to(cuda_device), 1.3).cpu(), oracle.temporal_sharpen(xh.float(), 1.3).to(dt))
+    # uint8 BGR wire format == decode -> spec -> encode
+    u8 = (xv * 255).to(torch.uint8).flip(-1).contiguous()
+    dec = oracle.frames_to_tensor(list(u8.numpy()))
+    enc = np.stack(oracle.tensor_to_frames(oracle.temporal_sharpen(dec, 1.3)))
+    assert np.array_equal(pkg.ops.temporal_sharpen(u8.to(cuda_device), 1.3).cpu().numpy(), enc)
+    # the node chunks a host clip and carries the neighbours along
+    node = pkg.NODE_CLASS_MAPPINGS["VRGDG_B200_TemporalSharpen"]()
+    assert torch.equal(node.sharpen(xv, 1.3, 2)[0], want) and torch.equal(node.sharpen(xv, 1.3, 0)[0], want)
+    with pytest.raises(ValueError):
+        pkg.ops.temporal_sharpen(d, 1.3, d[0, :10], None)
+
+
+def test_temporal_sharpen_full_size_config5_shape(pkg, cuda_device, oracle):
+    """configs[4] frame size (1080p fp32) at a reduced clip length against the spec oracle, plus size-independent properties"""
+    x = natural_frames(8, 1080, 1920, seed=73)
+    got = pkg.ops.temporal_sharpen(x.to(cuda_device), 0.5)
+    assert torch.equal(got.cpu(), oracle.temporal_sharpen(x, 0.5))
+    still = x[:1].repeat(6, 1, 1, 1).to(cuda_device)               # a still clip is a fixed point up to the rounding of (3x)/3
+    assert maxdiff(pkg.ops.temporal_sharpen(still, 2.0), still) <= 3e-7
+    assert torch.equal(pkg.ops.temporal_sharpen(x.to(cuda_device), 0.0).cpu(), x)      # strength 0 = identity

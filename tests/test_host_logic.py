@@ -16,9 +16,15 @@ def meta():
         return json.load(fh)
 
 
+EXTRA_KEYS = {"VRGDG_B200_PostChain", "VRGDG_B200_EnhanceFrames", "VRGDG_B200_TemporalSharpen"}      # this package's own nodes (no reference counterpart)
+
+
 def test_node_mappings_and_api_match_reference(pkg, meta):
-    assert set(pkg.NODE_CLASS_MAPPINGS) == set(meta["api"])
-    for key, want in meta["api"].items():
+    with open(os.path.join(GOLDEN, "reference_meta_r2.json"), encoding="utf-8") as fh:
+        meta2 = json.load(fh)                                              # the two "next"-row reference nodes (make_golden_r2.py)
+    api = dict(meta["api"], **meta2["api"])
+    assert set(pkg.NODE_CLASS_MAPPINGS) == set(api) | EXTRA_KEYS
+    for key, want in api.items():
         cls = pkg.NODE_CLASS_MAPPINGS[key]
         got = json.loads(json.dumps(cls.INPUT_TYPES()))
         if key == "VRGDG_LUTS":
@@ -30,7 +36,18 @@ def test_node_mappings_and_api_match_reference(pkg, meta):
         assert list(getattr(cls, "RETURN_NAMES", ())) == want["RETURN_NAMES"]
         assert getattr(cls, "DESCRIPTION", None) == want["DESCRIPTION"]
         assert callable(getattr(cls, cls.FUNCTION))
-    assert pkg.NODE_DISPLAY_NAME_MAPPINGS == meta["display_names"]
+        assert bool(getattr(cls, "OUTPUT_NODE", False)) == bool(want.get("OUTPUT_NODE", False))
+    names = dict(meta["display_names"], **meta2["display_names"])
+    assert {k: v for k, v in pkg.NODE_DISPLAY_NAME_MAPPINGS.items() if k not in EXTRA_KEYS} == names
+    for key in EXTRA_KEYS:                                                   # ComfyUI's node contract for the extra keys
+        cls = pkg.NODE_CLASS_MAPPINGS[key]
+        it = cls.INPUT_TYPES()
+        assert "images" in it["required"] and it["required"]["images"] == ("IMAGE",)
+        assert cls.RETURN_TYPES == ("IMAGE",) and callable(getattr(cls, cls.FUNCTION)) and isinstance(cls.CATEGORY, str)
+        assert key in pkg.NODE_DISPLAY_NAME_MAPPINGS
+        import inspect
+        params = list(inspect.signature(getattr(cls, cls.FUNCTION)).parameters)[1:]
+        assert params == list(it["required"]) + list(it.get("optional", {})), key      # widgets are passed by name, in this order
 
 
 def test_method_signatures_are_the_reference_ones(pkg):
