@@ -22,6 +22,7 @@ STENCIL_NONE, STENCIL_BOX_UNSHARP, STENCIL_LAPLACIAN_CPU, STENCIL_LAPLACIAN_GPU,
 BORDER_REPLICATE, BORDER_ZERO = 0, 1
 SEED_PER_CLIP, SEED_PER_FRAME = 0, 1
 CHAIN_FAST_MATH = 1
+CHAIN_CM_RECOMPUTE = 2
 
 
 class ChainDesc(ctypes.Structure):
@@ -109,6 +110,8 @@ SIGNATURES = {
     "vrgdg_chain_apply_ext": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _i, _vp]),
     "vrgdg_chain_lab_moments": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp, _i64, _vp]),
     "vrgdg_chain_lab_moments_ext": (_i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _vp, _vp, _i64, _vp]),
+    "vrgdg_chain_cm_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "vrgdg_chain_cm_apply": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ChainDesc), _vp, _i, _vp, _i, _vp, _i64, _i, _vp]),
     "vrgdg_adjust_scratch_bytes": (_i64, [_i, _i, _i, ctypes.POINTER(AdjustDesc)]),
     "vrgdg_adjust": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(AdjustDesc), _vp, _vp, _vp, _i64, _vp]),
     "vrgdg_resize": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ResizeDesc), _vp]),

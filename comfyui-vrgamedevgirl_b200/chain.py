@@ -27,6 +27,10 @@ class PostChain:
         self._lut_dev = None
         self._ref_sums = None
         self.timing = None          # set to a list to collect (moments_start, moments_end, apply_start, apply_end) CUDA events per call
+        # colour-match schedule (vrgdg_chain_cm_apply): one library call; `split` = the three-call path (statistics, parameters,
+        # apply as separate entry points; what `timing` needs), `recompute` / `group_frames`: see include/vrgdg_b200.h
+        self.split, self.recompute, self.group_frames = False, False, 0
+        self._scratch = None
         if lut is not None:
             self._lut_dev = ops.pack_lut(lut["lut_data"]["lut"], self.device)
         if colormatch is not None:
@@ -41,7 +45,7 @@ class PostChain:
         else:
             raise ValueError("colour match needs reference_image or ref_sums")
 
-    def _desc(self, frames, first_frame, keep, ext_noise=None):
+    def _desc(self, frames, first_frame, keep, ext_noise=None, fused_cm=False):
         d = nv.ChainDesc()
         if self.grain is not None:
             s = float(self.grain["saturation_mix"])
@@ -74,7 +78,11 @@ class PostChain:
             d.post_seed = int(self.post_grain.get("seed", 0)) & 0xFFFFFFFFFFFFFFFF
             d.post_frame0 = int(first_frame)
             d.post_seed_mode = int(self.post_grain.get("seed_mode", nv.SEED_PER_FRAME))
-        if self.colormatch is not None:
+        if self.colormatch is not None and fused_cm:
+            t = float(self.colormatch.get("strength", 1.0))
+            d.colormatch_enabled = 1
+            d.cm_t, d.cm_one_minus_t = t, 1.0 - t
+        elif self.colormatch is not None:
             # per-frame LAB moments of the colour-match INPUT (= grain output when grain is enabled): a first pass
             # that recomputes the counter-based grain instead of materialising it
             if self.timing is not None:
@@ -95,6 +103,11 @@ class PostChain:
         """frames: CUDA [B,H,W,3]; first_frame: absolute index of frames[0] in the clip (keys the grain).
         ext_noise (tests): N(0,1) tensor replacing the generator; fast_math then selects the production arithmetic."""
         keep = []
+        if self.colormatch is not None and not self.split and self.timing is None:
+            d = self._desc(frames, first_frame, keep, ext_noise, fused_cm=True)
+            res, self._scratch = ops.chain_cm_apply(frames, d, self._ref_sums, ext_noise=ext_noise, out=out, fast_math=fast_math,
+                                                    recompute=self.recompute, group_frames=self.group_frames, scratch=self._scratch)
+            return res
         d = self._desc(frames, first_frame, keep, ext_noise)
         if self.timing is None:
             return ops.chain_apply(frames, d, ext_noise=ext_noise, keepalive=keep, out=out, fast_math=fast_math)

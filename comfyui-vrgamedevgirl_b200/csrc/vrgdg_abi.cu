@@ -381,10 +381,11 @@ static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, Po
   return VRGDG_OK;
 }
 
-/* ext noise for the chain's first grain is passed through an environment-independent side door:
- * vrgdg_chain_apply_ext (test hook used by the parity tests, same kernels). */
-static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
-                            const void* ext_noise, bool fast, void* stream) {
+/* Core of the chain entry points.  from_f: `in` holds the (fx, fy, fz) planes the moments pass stored (fp32, same layout as the
+ * frames) and the grain + forward-Lab half of the colour match has already happened: stages become ST_CMF [| ST_LUT].
+ * cm_params (when non-null) replaces desc->cm_params; frame_offset is added to both grain frame indices (group scheduling). */
+static int chain_apply_core(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
+                            const void* ext_noise, bool fast, void* stream, const float* cm_params, bool from_f, int64_t frame_offset) {
   if (!d) return fail(VRGDG_E_INVALID, "vrgdg_chain_apply: null descriptor");
   int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_apply");
   if (rc) return rc;
@@ -398,8 +399,17 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
   memset(&Q, 0, sizeof(Q));
   int mask = 0;
   bool exact = true;
-  if ((rc = chain_point_params(d, B, H, W, Q.P, mask, exact, ext_noise, fast))) return rc;
-  const bool need_tile = d->stencil_op != VRGDG_STENCIL_NONE || d->post_grain_enabled;
+  vrgdg_chain_desc dd = *d;
+  if (cm_params) dd.cm_params = cm_params;
+  dd.grain_frame0 += frame_offset;
+  dd.post_frame0 += frame_offset;
+  if ((rc = chain_point_params(&dd, B, H, W, Q.P, mask, exact, ext_noise, fast))) return rc;
+  if (from_f) {
+    if (dtype != VRGDG_F32 || !(mask & ST_CM)) return fail(VRGDG_E_INVALID, "chain: the f-plane pass needs fp32 frames and colour match");
+    mask = (mask & ST_LUT) | ST_CMF;
+    Q.P.ext_noise = nullptr;
+  }
+  const bool need_tile = dd.stencil_op != VRGDG_STENCIL_NONE || dd.post_grain_enabled;
   if (!need_tile) {
     if (mask == 0) {   // nothing enabled: copy
       if (in != out) {
@@ -414,14 +424,19 @@ static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int 
     if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_apply");
     return VRGDG_OK;
   }
-  Q.op = d->stencil_op; Q.strength = d->stencil_strength; Q.border = d->stencil_border;
+  Q.op = dd.stencil_op; Q.strength = dd.stencil_strength; Q.border = dd.stencil_border;
   Q.exact_stencil = (exact && (dtype == VRGDG_F32 || dtype == VRGDG_U8BGR)) ? 1 : 0;
-  Q.post_enabled = d->post_grain_enabled ? 1 : 0;
-  Q.pI = d->post_intensity; Q.ps = d->post_sat; Q.poms = d->post_one_minus_sat;
-  Q.pseed = d->post_seed; Q.pframe0 = d->post_frame0; Q.pseed_mode = d->post_seed_mode;
+  Q.post_enabled = dd.post_grain_enabled ? 1 : 0;
+  Q.pI = dd.post_intensity; Q.ps = dd.post_sat; Q.poms = dd.post_one_minus_sat;
+  Q.pseed = dd.post_seed; Q.pframe0 = dd.post_frame0; Q.pseed_mode = dd.post_seed_mode;
   grain_make_key(Q.pseed, Q.pseed_mode, Q.pkey);
   if (Q.post_enabled && mask == 0) mask = ST_POST;    // pure stencil + post grain: one Philox call per pixel pair via the grain plane
   return run_tile(in, out, B, H, W, dtype, Q, mask, exact, ctx);
+}
+
+static int chain_apply_impl(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
+                            const void* ext_noise, bool fast, void* stream) {
+  return chain_apply_core(in, out, B, H, W, dtype, d, ext_noise, fast, stream, nullptr, false, 0);
 }
 
 int vrgdg_chain_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, void* stream) {
@@ -461,6 +476,98 @@ int vrgdg_chain_lab_moments(const void* in, int B, int H, int W, int dtype, cons
 int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc, const void* ext_noise,
                                 double* sums, void* scratch, int64_t scratch_bytes, void* stream) {
   return chain_moments_impl(in, B, H, W, dtype, desc, ext_noise, sums, scratch, scratch_bytes, stream, "vrgdg_chain_lab_moments_ext");
+}
+
+/* ---- one call for a chain WITH colour match ------------------------------------------------------------------------------
+ * scratch layout: [sums B x 7 doubles][params B x 12 floats, padded to 16 bytes][partials G x 296 x 6 doubles][f-planes G x H x W x 3 floats] */
+static int cm_group_frames(int B, int H, int W, int dtype, int flags, int group_frames) {
+  (void)dtype; (void)flags;
+  if (group_frames > 0) return group_frames < B ? group_frames : (B > 0 ? B : 1);
+  // Measured (profiles/README.md, round 2): both passes are instruction-issue bound, so keeping a group's re-read set inside L2
+  // (1-2 frames per group) buys nothing, while short launches lose 5-20 % to their last partial wave of tiles.  Default = about
+  // 64 Mpixel per group (8 x 4K, 32 x 1080p): > 25 000 tiles per launch, <= 800 MB of f-planes.
+  const int64_t px = (int64_t)H * W;
+  int64_t g = px > 0 ? (((int64_t)64 << 20) + px - 1) / px : 1;
+  if (g < 1) g = 1;
+  if (g > 64) g = 64;
+  return g < B ? (int)g : (B > 0 ? B : 1);
+}
+
+static bool cm_uses_planes(int dtype, int H, int W, const void* in, int flags) {
+  return dtype == VRGDG_F32 && !(flags & VRGDG_CHAIN_CM_RECOMPUTE) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+}
+
+int64_t vrgdg_chain_cm_scratch_bytes(int B, int H, int W, int dtype, int flags, int group_frames) {
+  if (B < 0 || H < 0 || W < 0 || !dtype_ok(dtype)) return 0;
+  const int g = cm_group_frames(B, H, W, dtype, flags, group_frames);
+  int64_t n = (int64_t)B * 7 * 8;
+  n += (((int64_t)B * 12 * 4 + 15) / 16) * 16;
+  n += (int64_t)g * MOMENT_BLOCKS * 6 * 8;
+  if (dtype == VRGDG_F32 && !(flags & VRGDG_CHAIN_CM_RECOMPUTE)) n += (int64_t)g * H * W * 3 * 4;
+  return n + 256;
+}
+
+int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
+                         const double* ref_sums, int n_ref, const void* ext_noise, int flags, void* scratch, int64_t scratch_bytes,
+                         int group_frames, void* stream) {
+  if (!desc) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: null descriptor");
+  if (!desc->colormatch_enabled) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: the descriptor has no colour-match stage (use vrgdg_chain_apply)");
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_cm_apply");
+  if (rc) return rc;
+  if (n_ref != 1 && n_ref != B) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: reference batch %d is neither 1 nor %d", n_ref, B);
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (!ref_sums || !scratch) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: null pointer");
+  if (in == out) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply cannot run in place");
+  if (reinterpret_cast<uintptr_t>(scratch) & 255u) return fail(VRGDG_E_ALIGN, "vrgdg_chain_cm_apply: scratch must be 256-byte aligned");
+  if (scratch_bytes < vrgdg_chain_cm_scratch_bytes(B, H, W, dtype, flags, group_frames))
+    return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: scratch too small (%lld < %lld)", (long long)scratch_bytes,
+                (long long)vrgdg_chain_cm_scratch_bytes(B, H, W, dtype, flags, group_frames));
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+  const int G = cm_group_frames(B, H, W, dtype, flags, group_frames);
+  const bool planes = cm_uses_planes(dtype, H, W, in, flags);
+  char* sp = reinterpret_cast<char*>(scratch);
+  double* sums = reinterpret_cast<double*>(sp);
+  sp += (int64_t)B * 7 * 8;
+  float* params = reinterpret_cast<float*>(sp);
+  sp += (((int64_t)B * 12 * 4 + 15) / 16) * 16;
+  double* partials = reinterpret_cast<double*>(sp);
+  sp += (int64_t)G * MOMENT_BLOCKS * 6 * 8;
+  sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(sp) + 255u) & ~(uintptr_t)255u);
+  float* fplanes = planes ? reinterpret_cast<float*>(sp) : nullptr;
+  const size_t es = elem_size(dtype);
+  const size_t frame_bytes = (size_t)H * W * 3 * es;
+  const size_t noise_es = (dtype == VRGDG_U8BGR) ? 4 : es;
+  const bool fast = (flags & VRGDG_CHAIN_FAST_MATH) != 0;
+  for (int g0 = 0; g0 < B; g0 += G) {
+    const int n = (B - g0 < G) ? B - g0 : G;
+    const char* gin = reinterpret_cast<const char*>(in) + (size_t)g0 * frame_bytes;
+    char* gout = reinterpret_cast<char*>(out) + (size_t)g0 * frame_bytes;
+    const void* gnoise = ext_noise ? reinterpret_cast<const char*>(ext_noise) + (size_t)g0 * H * W * 3 * noise_es : nullptr;
+    // pass 1: grain (recomputed from the counter-based generator or read from ext_noise) -> Lab statistics [+ f-planes]
+    PointParams P;
+    zero_point(P, n, H, W);
+    if (desc->grain_enabled) {
+      if (desc->grain_seed_mode != VRGDG_SEED_PER_CLIP && desc->grain_seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: bad grain seed_mode %d", desc->grain_seed_mode);
+      P.gI = desc->grain_intensity; P.gs = desc->grain_sat; P.goms = desc->grain_one_minus_sat;
+      P.seed = desc->grain_seed; P.frame0 = desc->grain_frame0 + g0; P.seed_mode = desc->grain_seed_mode;
+      grain_make_key(P.seed, P.seed_mode, P.gkey);
+      P.ext_noise = gnoise;
+    }
+#define MO(T) launch_moments<T>(gin, P, desc->grain_enabled != 0, 0, H, sums + (int64_t)g0 * 7, partials, ctx, fplanes)
+    cudaError_t e = DISPATCH_DTYPE(dtype, MO);
+#undef MO
+    if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (moments)");
+    k_colormatch_params<<<(n + 127) / 128, 128, 0, ctx.stream>>>(sums + (int64_t)g0 * 7, n, ref_sums + (n_ref == 1 ? 0 : (int64_t)g0 * 7), n_ref == 1 ? 1 : n,
+                                                                params + (int64_t)g0 * 12);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (params)");
+    // pass 2: the fused apply, from the f-planes (no grain, no forward Lab) or from the frames
+    rc = chain_apply_core(planes ? reinterpret_cast<const void*>(fplanes) : reinterpret_cast<const void*>(gin), gout, n, H, W, dtype, desc, gnoise, fast,
+                          stream, params + (int64_t)g0 * 12, planes, g0);
+    if (rc) return rc;
+  }
+  return VRGDG_OK;
 }
 
 int64_t vrgdg_adjust_scratch_bytes(int B, int H, int W, const vrgdg_adjust_desc* d) {

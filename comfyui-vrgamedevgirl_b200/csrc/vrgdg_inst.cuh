@@ -59,6 +59,15 @@ cudaError_t launch_point(const void* in, void* out, const PointParams& P, int ma
     return launch_point_v<T, M, true>(in, out, P, ctx);
   switch (mask) {
     VRGDG_PT(1) VRGDG_PT(2) VRGDG_PT(3) VRGDG_PT(4) VRGDG_PT(5) VRGDG_PT(6) VRGDG_PT(7)
+    case ST_CMF:                 // second pass of the f-plane schedule: input = (fx, fy, fz) planes, fp32 only
+      if constexpr (sizeof(T) == 4) return launch_point_v<T, ST_CMF, true>(in, out, P, ctx);
+      return cudaErrorInvalidValue;
+    case ST_CMF | ST_LUT:
+      if constexpr (sizeof(T) == 4) {
+        if (!exact) return launch_point_v<T, ST_CMF | ST_LUT, false>(in, out, P, ctx);
+        return launch_point_v<T, ST_CMF | ST_LUT, true>(in, out, P, ctx);
+      }
+      return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 #undef VRGDG_PT
@@ -114,6 +123,15 @@ cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, Tile
   switch (mask) {
     VRGDG_TL(0) VRGDG_TL(1) VRGDG_TL(2) VRGDG_TL(3) VRGDG_TL(4) VRGDG_TL(5) VRGDG_TL(6) VRGDG_TL(7)
     VRGDG_TL(8)     // stencil + post grain staged in a shared-memory plane (the enhancer chain)
+    case ST_CMF:
+      if constexpr (sizeof(T) == 4) return launch_tile_k<T, ST_CMF, true>(tmap, in, out, Q, ctx);
+      return cudaErrorInvalidValue;
+    case ST_CMF | ST_LUT:
+      if constexpr (sizeof(T) == 4) {
+        if (!exact) return launch_tile_k<T, ST_CMF | ST_LUT, false>(tmap, in, out, Q, ctx);
+        return launch_tile_k<T, ST_CMF | ST_LUT, true>(tmap, in, out, Q, ctx);
+      }
+      return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 #undef VRGDG_TL
@@ -122,19 +140,20 @@ cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, Tile
 // ---- moments -------------------------------------------------------------------------------------
 template <typename T>
 cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows, double* sums,
-                           double* partials, const LaunchCtx& ctx) {
+                           double* partials, const LaunchCtx& ctx, float* fplanes) {
   if (P.B == 0) return cudaSuccess;
   typedef typename Io<T>::word_t word_t;
   constexpr int PX = (int)(sizeof(word_t) / sizeof(T));
   const bool vec = (P.W % PX == 0) && ((reinterpret_cast<uintptr_t>(in) & (sizeof(word_t) - 1)) == 0);
+  if (fplanes && !(vec && sizeof(T) == 4 && aligned16(fplanes))) return cudaErrorInvalidValue;   // the ABI layer only asks for planes when this holds
   dim3 grid(MOMENT_BLOCKS, P.B);
   const T* src = reinterpret_cast<const T*>(in);
   if (grain) {
-    if (vec) k_lab_moments<T, true, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
-    else k_lab_moments<T, true, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+    if (vec) k_lab_moments<T, true, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
+    else k_lab_moments<T, true, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
   } else {
-    if (vec) k_lab_moments<T, false, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
-    else k_lab_moments<T, false, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials);
+    if (vec) k_lab_moments<T, false, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
+    else k_lab_moments<T, false, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
   }
   count_launch();
   cudaError_t e = cudaGetLastError();
@@ -166,7 +185,7 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_point<T>(const void*, void*, const PointParams&, int, bool, const LaunchCtx&);              \
   template cudaError_t launch_lut_rgba<T>(const void*, void*, int64_t, const LutParams&, const LaunchCtx&);               \
   template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
-  template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&); \
+  template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&, float*); \
   template cudaError_t launch_adjust<T>(const void*, void*, const AdjustParams&, int, float*, float*, const LaunchCtx&);              \
   template cudaError_t launch_resize<T>(const void*, void*, const ResizeParams&, const LaunchCtx&);                       \
   template cudaError_t launch_blend<T>(const void*, const void*, void*, int64_t, float, float, const LaunchCtx&);         \

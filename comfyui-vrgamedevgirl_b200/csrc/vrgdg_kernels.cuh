@@ -15,7 +15,13 @@
 
 namespace vrgdg {
 
-enum { ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4, ST_POST = 8 /* k_tile only: post-grain values staged in a shared-memory plane */ };
+enum {
+  ST_GRAIN = 1, ST_CM = 2, ST_LUT = 4,
+  ST_POST = 8,   /* k_tile only: post-grain values staged in a shared-memory plane */
+  ST_CMF = 16,   /* colour match whose input is NOT rgb but the (fx, fy, fz) planes the moments pass stored (fp32 frames only): the
+                    second pass of vrgdg_chain_cm_apply neither redraws the grain nor repeats the forward Lab transform */
+  ST_PRE = ST_GRAIN | ST_CM | ST_LUT | ST_CMF   /* per-pixel stages that run before the stencil */
+};
 
 // ---- element conversion -------------------------------------------------------------------------
 template <typename T> struct Elem;
@@ -86,6 +92,9 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const CmFold
   if (MASK & ST_CM) {
     colormatch_fold_pixel(r, g, b, cmf);
   }
+  if (MASK & ST_CMF) {
+    colormatch_from_f(r, g, b, cmf);          // (r, g, b) hold (fx, fy, fz) on entry
+  }
   if (MASK & ST_LUT) {
     float x0 = r, x1 = g, x2 = b;
     lut3d_eval<EXACT>(P.lut, r, g, b);
@@ -136,7 +145,7 @@ k_point(const T* __restrict__ in, T* __restrict__ out, PointParams P,
     const int64_t e0 = ((int64_t)frame * P.hw + pix0) * 3;
     const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
     CmFold cmf = {};                          // per-frame affine map of the colour match, folded with the strength (uniform per block)
-    if (MASK & ST_CM) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
+    if (MASK & (ST_CM | ST_CMF)) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
     const uint32_t y = GRAIN ? (uint32_t)pix0 / (uint32_t)P.W : 0u;
     const uint32_t x = GRAIN ? (uint32_t)pix0 - y * (uint32_t)P.W : 0u;
 
@@ -322,7 +331,7 @@ struct TileParams {
 // 4 elements per row (16-byte shared loads at a 16-byte lane stride are bank-conflict free; 32-byte strides are not).
 template <typename T, int MASK> struct TileCfg {
   static constexpr bool HEAVY = (MASK & ST_LUT) != 0;
-  static constexpr bool WORK = (sizeof(T) == 1) || (((MASK & 7) != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
+  static constexpr bool WORK = (sizeof(T) == 1) || (((MASK & ST_PRE) != 0) && (sizeof(T) != 4));   // uint8 frames always convert into the work tile
   static constexpr bool GPLANE = (MASK & ST_POST) != 0;   // grain of the post stage, one Philox call per pixel pair, kept in its own fp32 plane
   static constexpr int VEC = WORK ? 4 : 16 / (int)sizeof(T);   // output elements per thread per row
   static constexpr int BX = 256;                      // box width (elements) = TMA inner-dimension limit
@@ -535,7 +544,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, co
           o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
           o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
         }
-      } else if ((MASK & 7) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
+      } else if ((MASK & ST_PRE) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
     }
   } else {
@@ -561,7 +570,7 @@ __device__ __forceinline__ void stencil_rows(const T* raw, const float* work, co
           o[4 * q] = clamp01(fmaf(Q.pI, gv.x, o[4 * q])); o[4 * q + 1] = clamp01(fmaf(Q.pI, gv.y, o[4 * q + 1]));
           o[4 * q + 2] = clamp01(fmaf(Q.pI, gv.z, o[4 * q + 2])); o[4 * q + 3] = clamp01(fmaf(Q.pI, gv.w, o[4 * q + 3]));
         }
-      } else if ((MASK & 7) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
+      } else if ((MASK & ST_PRE) != 0 && Q.post_enabled) post_grain_elems<VEC, Io<T>::BGR>(Q, pgf, ge0, y, o);   // MASK 0 + post grain runs as ST_POST
       store_elems<T, VEC>(out, Q, frame, y, ge0, o);
 #pragma unroll
       for (int i = 0; i < WN; ++i) { w[0][i] = w[1][i]; w[1][i] = w[2][i]; }
@@ -689,14 +698,14 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
 
     // ---- per-pixel pre-stages over the halo tile (grain / colour match / LUT), result in fp32 ----
     // one task = one generator pixel pair (2 horizontally adjacent pixels): one Philox call, two independent LUT gathers in flight
-    if ((MASK & 7) != 0 || WORK || GPLANE) {
+    if ((MASK & ST_PRE) != 0 || WORK || GPLANE) {
       const PointParams& P = Q.P;
       constexpr bool GRAIN = (MASK & ST_GRAIN) != 0;
       constexpr bool BGR = Io<T>::BGR;
       typedef typename Io<T>::noise_t noise_t;
       const GrainFrame gf = grain_frame(P.seed, P.frame0, frame, P.seed_mode);
       CmFold cmf = {};
-      if (MASK & ST_CM) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
+      if (MASK & (ST_CM | ST_CMF)) cmf = cm_fold(P.cm_params + (int64_t)frame * 12, P.cm_t, P.cm_omt);
       const bool has_ext = GRAIN && (P.ext_noise != nullptr);
       const GrainFrame pgf = grain_frame(Q.pseed, Q.pframe0, frame, Q.pseed_mode);
       const int pair0 = x0e / 6 - 1;                        // pair holding the left halo pixel (x0e is a multiple of TXE, TXE of 6)
@@ -725,7 +734,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
           }
           pair_store6(gplane + so, kx > 0, gz);
         }
-        if ((MASK & 7) == 0 && !WORK) continue;               // nothing to do to the pixel values themselves
+        if ((MASK & ST_PRE) == 0 && !WORK) continue;               // nothing to do to the pixel values themselves
         float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (in_a | in_b) {
           pair_load6<T>(raw + so, kx > 0, e);
@@ -804,10 +813,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// u = (fy, fx - fy, fy - fz) of one pixel (Lab is an affine image of u, see cm_sums_to_lab_host)
-__device__ __forceinline__ void moments_add(float r, float g, float b, float* s1, float* s2) {
+// u = (fy, fx - fy, fy - fz) of one pixel (Lab is an affine image of u, see cm_sums_to_lab_host); (r, g, b) <- (fx, fy, fz)
+__device__ __forceinline__ void moments_add(float& r, float& g, float& b, float* s1, float* s2) {
   float fx, fy, fz;
   rgb_to_fxyz(r, g, b, fx, fy, fz);
+  r = fx; g = fy; b = fz;
   const float u1 = fx - fy, u2 = fy - fz;
   s1[0] += fy; s1[1] += u1; s1[2] += u2;
   s2[0] = fmaf(fy, fy, s2[0]); s2[1] = fmaf(u1, u1, s2[1]); s2[2] = fmaf(u2, u2, s2[2]);
@@ -815,9 +825,11 @@ __device__ __forceinline__ void moments_add(float r, float g, float b, float* s1
 
 // VEC: a thread moves 3 machine words = PX whole pixels per iteration (like k_point), one Philox call per pixel pair, the PX
 // pixels' sums are formed in fp32 (<= 8 terms) and then added to the thread's fp64 accumulators.  !VEC: one pixel per iteration.
+// fplanes != null (fp32 frames, VEC): the pass also stores (fx, fy, fz) of every pixel, [B][H][W][3] fp32 like the frames, for the
+// ST_CMF second pass.
 template <typename T, bool GRAIN, bool VEC>
 __global__ void __launch_bounds__(256)
-k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials) {
+k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials, float* __restrict__ fplanes) {
   typedef typename Io<T>::word_t word_t;
   typedef typename Io<T>::noise_t noise_t;
   constexpr bool BGR = Io<T>::BGR;
@@ -875,6 +887,14 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
     for (int j = 0; j < PX; ++j) moments_add(v[3 * j], v[3 * j + 1], v[3 * j + 2], s1, s2);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc[c] += (double)s1[c]; acc[3 + c] += (double)s2[c]; }
+    if constexpr (VEC && sizeof(T) == 4) {
+      if (fplanes != nullptr) {                  // uniform; v now holds (fx, fy, fz) per pixel
+        float4* dst = reinterpret_cast<float4*>(fplanes + ((int64_t)frame * P.hw + pif) * 3);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+      }
+    }
   }
   __shared__ double red[8][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -993,7 +1013,7 @@ template <typename T> cudaError_t launch_lut_rgba(const void* in, void* out, int
 template <typename T> cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, TileParams& Q, int mask,
                                               bool exact, const LaunchCtx& ctx);
 template <typename T> cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows,
-                                                 double* sums, double* partials, const LaunchCtx& ctx);
+                                                 double* sums, double* partials, const LaunchCtx& ctx, float* fplanes = nullptr);
 template <typename T> cudaError_t launch_u8_in(const uint8_t* in, void* out, int64_t npix, const LaunchCtx& ctx);
 template <typename T> cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const LaunchCtx& ctx);
 template <typename T> void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y);

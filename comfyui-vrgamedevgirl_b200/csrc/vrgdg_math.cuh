@@ -500,6 +500,14 @@ VRGDG_HD void colormatch_fold_pixel(float& r, float& g, float& b, const CmFold& 
   const float fz2 = fmaxf(fmaf(fz - fy, f.kb, fy2 - f.cb), 0.0f);
   fxyz_to_rgb(fx2, fy2, fz2, r, g, b);
 }
+// the same map applied to stored (fx, fy, fz): the second pass of the f-plane schedule
+VRGDG_HD void colormatch_from_f(float& r, float& g, float& b, const CmFold& f) {
+  const float fx = r, fy = g, fz = b;
+  const float fy2 = fmaf(fy, f.ky, f.cy);
+  const float fx2 = fmaf(fx - fy, f.ka, fy2 + f.ca);
+  const float fz2 = fmaxf(fmaf(fz - fy, f.kb, fy2 - f.cb), 0.0f);
+  fxyz_to_rgb(fx2, fy2, fz2, r, g, b);
+}
 VRGDG_HD void colormatch_pixel(float& r, float& g, float& b, const float* p, float t, float omt) {
   colormatch_fold_pixel(r, g, b, cm_fold(p, t, omt));
 }

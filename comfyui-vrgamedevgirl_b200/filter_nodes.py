@@ -89,11 +89,15 @@ class ColorMatchToReference:
         t = float(match_strength)
         with torch.cuda.device(dev):
             ref_sums = ops.lab_moments(reference_image.to(dev).to(images.dtype))
+        d = nv.ChainDesc()
+        d.colormatch_enabled, d.cm_t, d.cm_one_minus_t = 1, t, 1.0 - t
+        state = {"scratch": None}
         def run(frames, first):
-            sums = ops.lab_moments(frames)
+            # one library call per chunk: statistics, parameters and the apply pass (which starts from the stored Lab f-planes for
+            # fp32 frames instead of repeating the forward transform)
             rs = ref_sums if n_ref == 1 else ref_sums[first:first + frames.shape[0]]
-            params = ops.colormatch_params(sums, rs)
-            return ops.colormatch_apply(frames, params, t, 1.0 - t)
+            out, state["scratch"] = ops.chain_cm_apply(frames, d, rs, scratch=state["scratch"])
+            return out
         out = stream_frames(images, run, batch_size, result_device(images), dev)
         return (out,)
 

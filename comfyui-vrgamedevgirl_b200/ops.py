@@ -184,6 +184,35 @@ def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=
     return out
 
 
+def chain_cm_scratch(images, recompute=False, group_frames=0):
+    """Device scratch for chain_cm_apply on frames like `images` (reusable across calls with the same shape)."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    flags = nv.CHAIN_CM_RECOMPUTE if recompute else 0
+    nbytes = int(nv.load_library().vrgdg_chain_cm_scratch_bytes(B, H, W, nv.DTYPE_CODE[t.dtype], flags, int(group_frames)))
+    return torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=t.device)
+
+
+def chain_cm_apply(images, desc, ref_sums, ext_noise=None, out=None, fast_math=False, recompute=False, group_frames=0, scratch=None):
+    """A chain with colour match in ONE library call (vrgdg_chain_cm_apply): statistics, parameters and the fused apply, group by
+    group.  desc.colormatch_enabled / cm_t / cm_one_minus_t must be set; ref_sums: [1|B,7] float64 from lab_moments."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    out = torch.empty_like(t) if out is None else _check_out(out, t)
+    rs = ref_sums.to(device=t.device, dtype=torch.float64).reshape(-1, 7).contiguous()
+    flags = (nv.CHAIN_FAST_MATH if fast_math else 0) | (nv.CHAIN_CM_RECOMPUTE if recompute else 0)
+    lib = nv.load_library()
+    need = int(lib.vrgdg_chain_cm_scratch_bytes(B, H, W, nv.DTYPE_CODE[t.dtype], flags, int(group_frames)))
+    if scratch is None or scratch.numel() * scratch.element_size() < need or scratch.device != t.device:
+        scratch = torch.empty((max(need, 256),), dtype=torch.uint8, device=t.device)
+    n = _noise(ext_noise, t) if ext_noise is not None else None
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_chain_cm_apply(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], ctypes.byref(desc), nv.ptr(rs), int(rs.shape[0]),
+                                          nv.ptr(n), flags, nv.ptr(scratch), ctypes.c_int64(scratch.numel() * scratch.element_size()), int(group_frames),
+                                          nv.stream_ptr(t.device)))
+    return out, scratch
+
+
 def chain_lab_moments(images, desc, ext_noise=None):
     """LAB sums [B,7] of stage 1 (grain) of `desc` applied to images; ext_noise: the N(0,1) tensor a chain_apply(ext_noise=...) will use."""
     t = _frames(images)

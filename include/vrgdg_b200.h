@@ -195,6 +195,23 @@ VRGDG_API int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, i
                                 const vrgdg_chain_desc* desc, const void* ext_noise, double* sums,
                                 void* scratch, int64_t scratch_bytes, void* stream);
 
+/* One call for a chain that contains the colour-match stage (desc->colormatch_enabled; desc->cm_params is ignored): per-frame
+ * statistics of the colour-match input, parameters against ref_sums ([n_ref][7] doubles from vrgdg_lab_moments, n_ref 1 or B) and
+ * the fused apply, scheduled in groups of frames (bounds the scratch; see group_frames).
+ *   fp32 frames (default): pass 1 stores lab_f(XYZ/white) = (fx, fy, fz) of every pixel of the group in scratch ("f-planes",
+ *     12 B/px); pass 2 starts from them, so the grain is drawn once and the forward Lab transform evaluated once per pixel
+ *     (bit-identical to recomputing them: the stored values ARE the recomputed values).
+ *   other dtypes, or flags & VRGDG_CHAIN_CM_RECOMPUTE: pass 2 re-reads the frames and recomputes grain + forward Lab.
+ * group_frames: frames per group, 0 = about 64 Mpixel per group (8 x 4K, 32 x 1080p frames; at most 64): long enough launches
+ *     that their last partial wave of tiles does not matter; small groups (1-2 frames) keep the f-planes inside L2 instead.
+ * ext_noise / flags & VRGDG_CHAIN_FAST_MATH: as vrgdg_chain_apply_ext.  scratch: vrgdg_chain_cm_scratch_bytes() bytes of device
+ * memory, 256-byte aligned, owned by the caller (contents undefined afterwards).  Must not run in place. */
+#define VRGDG_CHAIN_CM_RECOMPUTE 2
+VRGDG_API int64_t vrgdg_chain_cm_scratch_bytes(int B, int H, int W, int dtype, int flags, int group_frames);
+VRGDG_API int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
+                         const double* ref_sums, int n_ref, const void* ext_noise, int flags,
+                         void* scratch, int64_t scratch_bytes, int group_frames, void* stream);
+
 /* ---- "adjust" pass of the Builder UI ---------------------------------------------------------------------------
  * Replaces _apply_adjust_tensor (VRGDG_LUTVideoTools.py:307-391): clamp, temperature/tint offset, exposure, contrast,
  * saturation, highlight/shadow/white/black masks, clarity (k x k reflect-padded box, k = min(9, odd(H), odd(W))), sharpen

@@ -125,6 +125,53 @@ def test_postchain_full_chain_on_reference_noise(pkg, cuda_device):
     assert torch.equal(pkg.ops.chain_lab_moments(x, d, ext_noise=z), pkg.ops.lab_moments(grained))
 
 
+def test_one_call_colormatch_chain_schedules_agree(pkg, cuda_device):
+    """vrgdg_chain_cm_apply: f-plane schedule (fp32), recompute schedule, any group size, and the three-call path give the same frames"""
+    nv = pkg._native
+    lut = _lut33(pkg)
+    ref = natural_frames(1, 50, 60, seed=21) * 0.8
+    for dt, W in ((torch.float32, 96), (torch.float32, 93), (torch.float16, 96), (torch.uint8, 96)):
+        x = natural_frames(5, 72, W, seed=20)
+        x = (x * 255).to(torch.uint8) if dt == torch.uint8 else x.to(dt)
+        x = x.to(cuda_device)
+        refd = (ref * 255).to(torch.uint8) if dt == torch.uint8 else ref.to(dt)
+        mk = lambda: pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(reference_image=refd, strength=0.8),
+                                         lut=dict(lut_data=lut, strength=10.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+        base = mk()
+        before = nv.launch_count()
+        fused = base(x, first_frame=7)
+        assert nv.launch_count() - before >= 4
+        three = mk()
+        three.split = True
+        want = three(x, first_frame=7)
+        rec = mk()
+        rec.recompute = True
+        assert torch.equal(rec(x, first_frame=7), want), dt                      # same kernels, grouped: bit-identical
+        tol = 0 if dt != torch.float32 else 2e-6                                # fp32: the f-plane pass (other dtypes always recompute)
+        assert maxdiff(fused.float(), want.float()) <= tol, (dt, W)
+        for g in (1, 2, 3):
+            c = mk()
+            c.group_frames = g
+            assert torch.equal(c(x, first_frame=7), fused), (dt, g)              # group size never changes a pixel
+        # shard invariance through the one-call path
+        assert torch.equal(mk()(x[2:].contiguous(), first_frame=9), fused[2:])
+    # colour match without LUT / stencil (streaming second pass) and one reference per frame (n_ref == B)
+    x = natural_frames(4, 40, 64, seed=22, device=cuda_device)
+    refs = natural_frames(4, 30, 44, seed=23, device=cuda_device)
+    ref_sums = pkg.ops.lab_moments(refs)
+    d = nv.ChainDesc()
+    d.colormatch_enabled, d.cm_t, d.cm_one_minus_t = 1, 1.0, 0.0
+    got, _ = pkg.ops.chain_cm_apply(x, d, ref_sums, group_frames=3)
+    want = pkg.ops.colormatch_apply(x, pkg.ops.colormatch_params(pkg.ops.lab_moments(x), ref_sums), 1.0, 0.0)
+    assert maxdiff(got, want) <= 2e-6
+    got_r, _ = pkg.ops.chain_cm_apply(x, d, ref_sums, recompute=True)
+    assert torch.equal(got_r, want)
+    with pytest.raises(ValueError):
+        pkg.ops.chain_cm_apply(x, nv.ChainDesc(), ref_sums)                      # no colour-match stage in the descriptor
+    with pytest.raises(ValueError):
+        pkg.ops.chain_cm_apply(x, d, ref_sums[:3])                               # reference batch neither 1 nor B
+
+
 def test_moments_vector_and_scalar_paths_agree(pkg, cuda_device, oracle):
     """W % 4 == 0 takes the 48-byte vector path, odd widths the scalar one; both against the oracle, with and without grain"""
     for W in (64, 61):

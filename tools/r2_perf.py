@@ -55,7 +55,7 @@ def lut33():
 
 def rows_cm():
     lut = lut33()
-    for (B, H, W, dt, tag) in ((4, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float32, "1080p_f32"), (8, 2160, 3840, torch.float16, "4k_f16")):
+    for (B, H, W, dt, tag) in ((8, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float32, "1080p_f32"), (8, 2160, 3840, torch.float16, "4k_f16")):
         x = natural_frames(B, H, W, seed=1, dtype=dt, device=dev)
         out = torch.empty_like(x)
         npix, bpp = B * H * W, 2 * 3 * x.element_size()
@@ -71,6 +71,23 @@ def rows_cm():
         full = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(ref_sums=ref_sums, strength=1.0),
                                    lut=dict(lut_data=lut, strength=10.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=dev)
         report(f"full_chain_g_cm_l_u/{tag}", timeit(lambda: full(x, out=out)), npix, bpp)
+        for g in (1, 2, 4, 8):
+            if g > B:
+                continue
+            full.group_frames = g
+            report(f"full_chain_g_cm_l_u/{tag}/planes_G{g}", timeit(lambda: full(x, out=out)), npix, bpp)
+            full.recompute = True
+            report(f"full_chain_g_cm_l_u/{tag}/recompute_G{g}", timeit(lambda: full(x, out=out)), npix, bpp)
+            full.recompute = False
+        full.group_frames, full.split = 0, True
+        report(f"full_chain_g_cm_l_u/{tag}/three_calls", timeit(lambda: full(x, out=out)), npix, bpp)
+        full.split = False
+        cmonly = pkg.chain.PostChain(colormatch=dict(ref_sums=ref_sums, strength=1.0), device=dev)
+        for g in (0, 1, 2, 4):
+            cmonly.group_frames = g
+            report(f"colormatch_one_call/{tag}/planes_G{g}", timeit(lambda: cmonly(x, out=out)), npix, bpp)
+        cmonly.recompute, cmonly.group_frames = True, 1
+        report(f"colormatch_one_call/{tag}/recompute_G1", timeit(lambda: cmonly(x, out=out)), npix, bpp)
         cmu = pkg.chain.PostChain(colormatch=dict(ref_sums=ref_sums, strength=1.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=dev)
         report(f"chain_cm_u/{tag}", timeit(lambda: cmu(x, out=out)), npix, bpp)
         del x, out, node

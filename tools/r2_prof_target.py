@@ -1,5 +1,5 @@
 """ncu target of round 2 (GPU box only): runs one workload a few times.
-    python tools/r2_prof_target.py {full|glu|cmu|moments|cmnode} {f32|f16} H W frames"""
+    python tools/r2_prof_target.py {full|glu|cmu|cmg1|moments|cmnode} {f32|f16} H W frames"""
 import importlib
 import os
 import sys
@@ -31,6 +31,10 @@ elif what == "glu":
     fn = lambda: c(x, out=out)
 elif what == "cmu":
     c = pkg.chain.PostChain(colormatch=dict(ref_sums=ref_sums, strength=1.0), stencil=S, device=dev)
+    fn = lambda: c(x, out=out)
+elif what == "cmg1":       # colour match alone, one frame per group: the f-planes of a group stay in L2 between the two passes
+    c = pkg.chain.PostChain(colormatch=dict(ref_sums=ref_sums, strength=1.0), device=dev)
+    c.group_frames = int(os.environ.get("VRGDG_G", "1"))
     fn = lambda: c(x, out=out)
 elif what == "moments":
     d = nv.ChainDesc()
