@@ -11,32 +11,42 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 pkg = importlib.import_module("comfyui-vrgamedevgirl_b200")
 from helpers import LUTS, natural_frames  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from _clocks import Clocks  # noqa: E402
+CLK = Clocks(0)
 
 nv, ops = pkg._native, pkg.ops
 dev = torch.device("cuda", 0)
 PEAK = 6573.5
 
 
+LAST_CLOCKS = [None]
+
+
 def timeit(fn, iters=10, warm=3):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(warm):
         fn()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        fn()
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ts.sort()
-    return ts[len(ts) // 2]
+
+    def run():
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+    ms, LAST_CLOCKS[0] = CLK.sample_while(run)      # NVML SM clock + throttle reasons sampled during the timed loop
+    return ms
 
 
 def report(name, ms, npix, bpp):
     gbs = npix * bpp / ms / 1e6
-    print(json.dumps({"kernel": name, "ms": round(ms, 4), "MP/s": round(npix / ms / 1e3, 1), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 3)}), flush=True)
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "MP/s": round(npix / ms / 1e3, 1), "GB/s": round(gbs, 1), "frac_hbm": round(gbs / PEAK, 3), "clocks": LAST_CLOCKS[0]}), flush=True)
 
 
 def main():
