@@ -2,7 +2,7 @@
 
 * VRGDGVideoEnhanceRestoreOriginal, VRGDGStandaloneVideoEnhancer: the REFERENCE's node keys, INPUT_TYPES, RETURN_* and method
   signatures (VRGDG_VideoEnhanceNodes.py:378-437, VRGDG_StandaloneVideoEnhancerNodes.py:869-903), so saved workflows load unchanged.
-* VRGDG_B200_PostChain, VRGDG_B200_EnhanceFrames, VRGDG_B200_TemporalSharpen: EXTRA keys (nothing in the reference has them).  A workflow that chains
+* VRGDG_B200_PostChain, VRGDG_B200_EnhanceFrames, VRGDG_B200_TemporalSharpen, VRGDG_B200_HistogramColorMatch: EXTRA keys (nothing in the reference has them).  A workflow that chains
   FastFilmGrain -> ColorMatchToReference -> VRGDG_LUTS -> FastUnsharpSharpen as four nodes pays four launches and, with ComfyUI's
   CPU intermediate device, four PCIe round trips; VRGDG_B200_PostChain is the same arithmetic (same widgets, same order) as ONE
   upload, the fused kernels, one download.  bench.py reports both (`e2e` and `e2e.stock_nodes`).
@@ -120,6 +120,44 @@ class VRGDG_B200_EnhanceFrames:
         return (stream_frames(images, fn, 8, result_device(images), dev),)
 
 
+class VRGDG_B200_HistogramColorMatch:
+    """Histogram / CDF colour transfer to one reference image: per-channel 256-bin histograms, monotone CDF mapping (the colour-match
+    mode BASELINE.json describes).  An extension of this package: the reference's ColorMatchToReference is the LAB mean/std transfer
+    and stays that; the arithmetic of this mode is specified in include/vrgdg_b200.h (vrgdg_hist_counts ...)."""
+
+    @classmethod
+    def INPUT_TYPES(cls):
+        return {
+            "required": {
+                "images": ("IMAGE",),
+                "reference_image": ("IMAGE",),
+                "match_strength": ("FLOAT", {"default": 1.0, "min": 0.0, "max": 1.0, "step": 0.01}),
+                "batch_size": ("INT", {"default": 8, "min": 0, "max": 500, "step": 1}),
+            }
+        }
+
+    RETURN_TYPES = ("IMAGE",)
+    FUNCTION = "match_histogram"
+    CATEGORY = "video/enhancement"
+    DESCRIPTION = "Matches each frame's per-channel histogram to a reference image (monotone CDF transfer, B200)."
+
+    def match_histogram(self, images, reference_image, match_strength, batch_size):
+        from . import ops
+        images = _as_frames(images)
+        ref = _as_frames(reference_image, "reference_image")
+        if int(ref.shape[0]) != 1:
+            raise ValueError("VRGDG_B200_HistogramColorMatch: reference_image must hold exactly one frame")
+        dev = compute_device(images)
+        t = float(match_strength)
+        with torch.cuda.device(dev):
+            ref_counts = ops.hist_counts(ref.to(dev).to(images.dtype))
+
+        def run(frames, first):
+            tables = ops.histmatch_tables(ops.hist_counts(frames), ref_counts)
+            return ops.histmatch_apply(frames, tables, t, 1.0 - t)
+        return (stream_frames(images, run, batch_size, result_device(images), dev),)
+
+
 class VRGDG_B200_TemporalSharpen:
     """3-frame temporal unsharp over an IMAGE batch read as a clip (BASELINE.json configs[4]).  An extension of this package: the
     reference has no temporal operator, the arithmetic is specified in include/vrgdg_b200.h (vrgdg_temporal_sharpen)."""
@@ -226,6 +264,7 @@ NODE_CLASS_MAPPINGS = {
     "VRGDG_B200_PostChain": VRGDG_B200_PostChain,
     "VRGDG_B200_EnhanceFrames": VRGDG_B200_EnhanceFrames,
     "VRGDG_B200_TemporalSharpen": VRGDG_B200_TemporalSharpen,
+    "VRGDG_B200_HistogramColorMatch": VRGDG_B200_HistogramColorMatch,
 }
 NODE_DISPLAY_NAME_MAPPINGS = {
     "VRGDGVideoEnhanceRestoreOriginal": "Video Enhance - Restore Original Resolution",
@@ -233,4 +272,5 @@ NODE_DISPLAY_NAME_MAPPINGS = {
     "VRGDG_B200_PostChain": "VRGDG B200 Post Chain (grain + colour match + LUT + sharpen, fused)",
     "VRGDG_B200_EnhanceFrames": "VRGDG B200 Enhance Frames (unsharp + seeded grain, fused)",
     "VRGDG_B200_TemporalSharpen": "VRGDG B200 Temporal Sharpen (3-frame)",
+    "VRGDG_B200_HistogramColorMatch": "VRGDG B200 Histogram Color Match (CDF transfer)",
 }

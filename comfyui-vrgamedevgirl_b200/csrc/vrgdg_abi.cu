@@ -7,6 +7,7 @@
 #include "vrgdg_resize.cuh"
 #include "vrgdg_lanczos.cuh"
 #include "vrgdg_temporal.cuh"
+#include "vrgdg_histmatch.cuh"
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
@@ -653,6 +654,57 @@ int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, f
   cudaError_t e = (dtype == VRGDG_F32) ? BL(float) : ((dtype == VRGDG_F16) ? BL(__half) : BL(__nv_bfloat16));
 #undef BL
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_blend");
+  return VRGDG_OK;
+}
+
+/* ---- histogram / CDF colour transfer (labelled extension, see vrgdg_histmatch.cuh) ---- */
+int vrgdg_hist_counts(const void* in, int B, int H, int W, int dtype, int row0, int rows, uint32_t* counts, void* stream) {
+  if (!dtype_ok(dtype)) return fail(VRGDG_E_INVALID, "vrgdg_hist_counts: unknown dtype %d", dtype);
+  if (B < 0 || H <= 0 || W <= 0) return fail(VRGDG_E_INVALID, "vrgdg_hist_counts: bad shape [%d,%d,%d]", B, H, W);
+  if (row0 < 0 || rows < 0 || row0 + rows > H) return fail(VRGDG_E_INVALID, "vrgdg_hist_counts: row range [%d,%d) outside [0,%d)", row0, row0 + rows, H);
+  if ((int64_t)H * W >= (int64_t)1 << 31) return fail(VRGDG_E_UNSUPPORTED, "vrgdg_hist_counts: frame of %d x %d pixels exceeds 2^31 (32-bit counters)", H, W);
+  if (B == 0) return VRGDG_OK;
+  if (!in || !counts) return fail(VRGDG_E_INVALID, "vrgdg_hist_counts: null pointer");
+  if (reinterpret_cast<uintptr_t>(counts) & 3u) return fail(VRGDG_E_ALIGN, "vrgdg_hist_counts: counts must be 4-byte aligned");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+#define HC(T) launch_hist_counts<T>(in, B, H, W, row0, rows, counts, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, HC);
+#undef HC
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_hist_counts");
+  return VRGDG_OK;
+}
+
+int vrgdg_histmatch_tables(const uint32_t* frame_counts, int B, const uint32_t* ref_counts, int n_ref, float* tables, void* stream) {
+  if (B < 0) return fail(VRGDG_E_INVALID, "vrgdg_histmatch_tables: negative B");
+  if (B == 0) return VRGDG_OK;
+  if (!frame_counts || !ref_counts || !tables) return fail(VRGDG_E_INVALID, "vrgdg_histmatch_tables: null pointer");
+  if (n_ref != 1 && n_ref != B) return fail(VRGDG_E_INVALID, "vrgdg_histmatch_tables: reference batch %d is neither 1 nor %d", n_ref, B);
+  if (reinterpret_cast<uintptr_t>(tables) & 7u) return fail(VRGDG_E_ALIGN, "vrgdg_histmatch_tables: tables must be 8-byte aligned");
+  LaunchCtx ctx;
+  int rc = get_ctx(stream, ctx);
+  if (rc) return rc;
+  k_hist_tables<<<B * 3, 256, 0, ctx.stream>>>(frame_counts, ref_counts, n_ref, reinterpret_cast<float2*>(tables));
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_histmatch_tables");
+  return VRGDG_OK;
+}
+
+int vrgdg_histmatch_apply(const void* in, void* out, int B, int H, int W, int dtype, const float* tables, float t, float one_minus_t,
+                          void* stream) {
+  int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_histmatch_apply");
+  if (rc) return rc;
+  if ((int64_t)B * H * W == 0) return VRGDG_OK;
+  if (!tables) return fail(VRGDG_E_INVALID, "vrgdg_histmatch_apply: null tables");
+  if (reinterpret_cast<uintptr_t>(tables) & 7u) return fail(VRGDG_E_ALIGN, "vrgdg_histmatch_apply: tables must be 8-byte aligned");
+  LaunchCtx ctx;
+  if ((rc = get_ctx(stream, ctx))) return rc;
+#define HA(T) launch_histmatch_apply<T>(in, out, B, (int64_t)H * W, reinterpret_cast<const float2*>(tables), t, one_minus_t, ctx)
+  cudaError_t e = DISPATCH_DTYPE(dtype, HA);
+#undef HA
+  if (e != cudaSuccess) return fail_cuda(e, "vrgdg_histmatch_apply");
   return VRGDG_OK;
 }
 

@@ -5,6 +5,7 @@
 #include "vrgdg_adjust.cuh"
 #include "vrgdg_resize.cuh"
 #include "vrgdg_temporal.cuh"
+#include "vrgdg_histmatch.cuh"
 #include <string.h>
 #include <stdlib.h>
 
@@ -190,6 +191,8 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_resize<T>(const void*, void*, const ResizeParams&, const LaunchCtx&);                       \
   template cudaError_t launch_blend<T>(const void*, const void*, void*, int64_t, float, float, const LaunchCtx&);         \
   template cudaError_t launch_temporal<T>(const void*, void*, const TemporalParams&, const LaunchCtx&);                   \
+  template cudaError_t launch_hist_counts<T>(const void*, int, int, int, int, int, uint32_t*, const LaunchCtx&);          \
+  template cudaError_t launch_histmatch_apply<T>(const void*, void*, int, int64_t, const float2*, float, float, const LaunchCtx&); \
   template void tile_geometry<T>(int, int, int&, int&, int&, int&);
 
 #define VRGDG_INSTANTIATE_CODECS(T)                                                                                       \

@@ -45,6 +45,30 @@ def reference_sums_distributed(reference_image, moments_fn=None, group=None):
     return total
 
 
+def reference_histogram_distributed(reference_image, counts_fn=None, group=None):
+    """256-bin RGB counts [1,3,256] int32 of a [1,H,W,3] reference image for the histogram colour-match mode (an extension of this
+    package; BASELINE.json: "NCCL all-gather for the global reference histogram"): rows sharded like reference_sums_distributed,
+    one all-gather of 3 x 256 counters per rank, summed.  Integer counts: identical on every rank and for every world size."""
+    if counts_fn is None:
+        from . import ops
+        counts_fn = lambda img, r0, n: ops.hist_counts(img, r0, n)
+    H = int(reference_image.shape[1])
+    if not (dist.is_available() and dist.is_initialized()):
+        return counts_fn(reference_image, 0, H)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r0, r1 = row_range(H, rank, world)
+    if r1 > r0:
+        mine = counts_fn(reference_image, r0, r1 - r0).reshape(1, 3, 256).to(torch.int32).contiguous()
+    else:
+        mine = torch.zeros(1, 3, 256, dtype=torch.int32, device=reference_image.device if reference_image.device.type == "cuda" else "cpu")
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    total = torch.zeros_like(mine)
+    for part in gathered:
+        total += part
+    return total
+
+
 def exchange_halo_frames(frames, group=None):
     """(prev, next) = the last frame of the previous rank and the first frame of the next rank ([H,W,3] each, None at the clip's
     ends) for the temporal 3-frame stencil (configs[4], an extension without a reference counterpart): one frame sent to each

@@ -285,6 +285,49 @@ def blend(a, b, weight_a, weight_b):
     return out
 
 
+def hist_counts(images, row0=0, rows=None):
+    """Per-frame, per-channel (R, G, B) 256-bin counts over rows [row0,row0+rows): int32 [B,3,256] (histogram colour match, a labelled
+    extension: vrgdg_hist_counts).  Counts are exact, so row-sharded counts of one image add up to the whole image's."""
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    rows = H - row0 if rows is None else rows
+    counts = torch.empty((B, 3, 256), dtype=torch.int32, device=t.device)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_hist_counts(nv.ptr(t), B, H, W, nv.DTYPE_CODE[t.dtype], int(row0), int(rows), nv.ptr(counts), nv.stream_ptr(t.device)))
+    return counts
+
+
+def histmatch_tables(frame_counts, ref_counts):
+    """[B,3,256] + [1|B,3,256] int32 counts -> [B,3,256,2] float32 {T[k], T[k+1]-T[k]}: the monotone map ref_CDF^-1(frame_CDF)."""
+    fc = frame_counts.contiguous()
+    rc = ref_counts.to(fc.device).contiguous()
+    if fc.dtype != torch.int32 or rc.dtype != torch.int32 or fc.ndim != 3 or fc.shape[1:] != (3, 256) or rc.ndim != 3 or rc.shape[1:] != (3, 256):
+        raise ValueError("vrgdg_b200: histogram counts must be int32 [n,3,256]")
+    if fc.device.type != "cuda":
+        raise RuntimeError("vrgdg_b200: histogram counts must live on a CUDA device")
+    B = int(fc.shape[0])
+    tables = torch.empty((B, 3, 256, 2), dtype=torch.float32, device=fc.device)
+    lib = nv.load_library()
+    with torch.cuda.device(fc.device):
+        nv.check(lib.vrgdg_histmatch_tables(nv.ptr(fc), B, nv.ptr(rc), int(rc.shape[0]), nv.ptr(tables), nv.stream_ptr(fc.device)))
+    return tables
+
+
+def histmatch_apply(images, tables, t_strength, one_minus_t):
+    t = _frames(images)
+    B, H, W, _ = t.shape
+    tb = tables.contiguous()
+    if tb.dtype != torch.float32 or tuple(tb.shape) != (B, 3, 256, 2) or tb.device != t.device:
+        raise ValueError("vrgdg_b200: tables must be float32 [B,3,256,2] on the images' device")
+    out = torch.empty_like(t)
+    lib = nv.load_library()
+    with torch.cuda.device(t.device):
+        nv.check(lib.vrgdg_histmatch_apply(nv.ptr(t), nv.ptr(out), B, H, W, nv.DTYPE_CODE[t.dtype], nv.ptr(tb), _f32(t_strength), _f32(one_minus_t),
+                                           nv.stream_ptr(t.device)))
+    return out
+
+
 def temporal_sharpen(images, strength, prev_frame=None, next_frame=None):
     """3-frame temporal unsharp over a clip [T,H,W,3] (configs[4]; labelled extension, see vrgdg_temporal_sharpen).  prev_frame /
     next_frame: [H,W,3] (or [1,H,W,3]) neighbours of the first / last frame when the clip is a shard of a longer one."""

@@ -253,6 +253,20 @@ VRGDG_API int vrgdg_resize(const void* in, void* out, int B, int Hs, int Ws, int
 VRGDG_API int vrgdg_blend(const void* a, const void* b, void* out, int64_t n, int dtype, float weight_a, float weight_b,
                 void* stream);
 
+/* ---- histogram / CDF colour transfer — LABELLED EXTENSION, no reference counterpart ---------------------------------------------
+ * BASELINE.json's north_star and configs[2] describe colour match as a "two-pass per-channel histogram + monotone-CDF LUT mapping";
+ * the reference's ColorMatchToReference is the LAB mean/std transfer above and holds no histogram.  This mode is
+ * therefore specified here (csrc/vrgdg_histmatch.cuh has the formulas), parity "unpinned":
+ *   vrgdg_hist_counts      per frame and RGB channel 256-bin counts over rows [row0,row0+rows) -> counts[B][3][256] uint32 (the call
+ *                          zeroes them first; exact integers, so row-sharded reference counts from several ranks simply add)
+ *   vrgdg_histmatch_tables per frame and channel the monotone map reference_CDF^-1(frame_CDF) at the 257 bin edges ->
+ *                          tables[B][3][256][2] fp32 = {T[k], T[k+1]-T[k]}; n_ref = 1 (one reference for all frames) or B
+ *   vrgdg_histmatch_apply  out = clamp(x*(1-t) + map(x)*t), map = piecewise-linear interpolation of T */
+VRGDG_API int vrgdg_hist_counts(const void* in, int B, int H, int W, int dtype, int row0, int rows, uint32_t* counts, void* stream);
+VRGDG_API int vrgdg_histmatch_tables(const uint32_t* frame_counts, int B, const uint32_t* ref_counts, int n_ref, float* tables, void* stream);
+VRGDG_API int vrgdg_histmatch_apply(const void* in, void* out, int B, int H, int W, int dtype, const float* tables,
+                          float t, float one_minus_t, void* stream);
+
 /* ---- temporal 3-frame unsharp (BASELINE.json configs[4]) — LABELLED EXTENSION, no reference counterpart --------------------
  * The reference has no temporal operator (VRGDG_VideoEnhanceNodes.py holds no sharpen / blur / stencil), so the
  * specification is this library's:  out[t] = clamp(x[t] + s * (x[t] - (x[t-1] + x[t] + x[t+1]) / 3), 0, 1), fp32, one rounding

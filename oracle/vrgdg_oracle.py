@@ -560,6 +560,72 @@ def chain_full(images, noise, grain_intensity, saturation_mix, reference_image, 
     return unsharp_numpy(x, sharpen_strength)
 
 
+def hist_counts(images):
+    """256-bin counts per frame and RGB channel: bin = min(floor(clip(v,0,1) * 256), 255) evaluated in fp32.  int64 [B,3,256]."""
+    x = images.detach().cpu().float().numpy()
+    u = np.clip(x, np.float32(0.0), np.float32(1.0)) * np.float32(256.0)
+    k = np.minimum(u.astype(np.int64), 255)
+    B = x.shape[0]
+    out = np.zeros((B, 3, 256), dtype=np.int64)
+    for b in range(B):
+        for c in range(3):
+            out[b, c] = np.bincount(k[b, ..., c].ravel(), minlength=256)
+    return torch.from_numpy(out)
+
+
+def histmatch_tables(frame_counts, ref_counts):
+    """Edge tables T[0..256] = ref_CDF^-1(frame_CDF(edge)) with both CDFs piecewise linear over the bin edges.  NOT a restatement of
+    reference code (the reference has no histogram colour match): this IS the specification of the extension (parity
+    unpinned).  float32 [B,3,257]."""
+    fc = frame_counts.numpy().astype(np.int64)
+    rc = ref_counts.numpy().astype(np.int64)
+    B = fc.shape[0]
+    T = np.zeros((B, 3, 257), dtype=np.float32)
+    for b in range(B):
+        for c in range(3):
+            cf = np.cumsum(fc[b, c])
+            cr = np.cumsum(rc[0 if rc.shape[0] == 1 else b, c])
+            nf, nr = int(cf[-1]), int(cr[-1])
+            for e in range(257):
+                if nf == 0 or nr == 0:
+                    T[b, c, e] = np.float32(e / 256.0)
+                    continue
+                cq = 0 if e == 0 else int(cf[e - 1])
+                g = lambda i: (0 if i == 0 else int(cr[i - 1])) * nf          # edge values of the reference CDF, scaled: exact integers
+                rhs = cq * nr
+                ilo = next(i for i in range(257) if g(i) >= rhs)
+                if g(ilo) == rhs:                                              # q lies ON edges ilo..ihi (plateau): inverse closest to the source edge
+                    ihi = max(i for i in range(ilo, 257) if g(i) <= rhs)
+                    T[b, c, e] = np.float32(np.float64(min(max(e, ilo), ihi)) / np.float64(256.0))
+                else:                                                          # strictly inside the rising segment of bin j
+                    j = ilo - 1
+                    q = np.float64(cq) / np.float64(nf)
+                    prev = np.float64(cr[j - 1]) / np.float64(nr) if j > 0 else np.float64(0.0)
+                    cur = np.float64(cr[j]) / np.float64(nr)
+                    frac = (q - prev) / (cur - prev)
+                    T[b, c, e] = np.float32((np.float64(j) + frac) / np.float64(256.0))
+    return torch.from_numpy(T)
+
+
+def hist_match(images, reference_image, strength):
+    """Histogram / CDF colour transfer (extension; see histmatch_tables): out = clip(x*(1-t) + map(x)*t), fp32, one rounding per op."""
+    x = images.detach().cpu().float().numpy()
+    T = histmatch_tables(hist_counts(images), hist_counts(reference_image)).numpy()
+    t = np.float32(strength)
+    omt = np.float32(1.0 - float(strength))
+    u = np.clip(x, np.float32(0.0), np.float32(1.0)) * np.float32(256.0)
+    k = np.minimum(u.astype(np.int64), 255)
+    w = u - k.astype(np.float32)
+    out = np.empty_like(x)
+    for b in range(x.shape[0]):
+        for c in range(3):
+            t0 = T[b, c][k[b, ..., c]]
+            dt = (T[b, c][1:] - T[b, c][:-1]).astype(np.float32)[k[b, ..., c]]
+            m = (w[b, ..., c].astype(np.float64) * dt.astype(np.float64) + t0.astype(np.float64)).astype(np.float32)     # one FMA: exact product, one rounding
+            out[b, ..., c] = np.clip(x[b, ..., c] * omt + m * t, np.float32(0.0), np.float32(1.0))
+    return torch.from_numpy(out)
+
+
 def temporal_sharpen(frames, strength, prev_frame=None, next_frame=None):
     """configs[4] temporal 3-frame unsharp.  NOT a restatement of reference code: the reference has no temporal operator,
     so this NumPy function IS the specification (parity unpinned):

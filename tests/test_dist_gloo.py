@@ -25,6 +25,12 @@ def _cpu_moments(image, row0, rows):
     return oracle.lab_moments_f64(image[:, row0:row0 + rows])
 
 
+def oracle_counts(image):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vrgdg_oracle as oracle
+    return oracle.hist_counts(image).to(torch.int32)
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -38,10 +44,11 @@ def _worker(rank, world, port, out_dir):
         sums = d.reference_sums_distributed(ref, moments_fn=_cpu_moments)
         tiny = natural_frames(1, 1, 9, seed=4)             # fewer rows than ranks: one rank contributes zeros
         sums_tiny = d.reference_sums_distributed(tiny, moments_fn=_cpu_moments)
+        hist = d.reference_histogram_distributed(ref, counts_fn=lambda img, r0, n: oracle_counts(img[:, r0:r0 + n]))
         clip = natural_frames(5, 6, 8, seed=9)                # temporal stencil: one halo frame per shard boundary
         a, b = d.shard_range(5, rank, world)
         prev, nxt = d.exchange_halo_frames(clip[a:b])
-        torch.save({"sums": sums, "tiny": sums_tiny, "range": d.shard_range(11, rank, world), "prev": prev, "next": nxt, "span": (a, b)},
+        torch.save({"sums": sums, "tiny": sums_tiny, "range": d.shard_range(11, rank, world), "prev": prev, "next": nxt, "span": (a, b), "hist": hist},
                    os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -59,6 +66,7 @@ def test_reference_sums_allgather_two_ranks(tmp_path, oracle):
     assert torch.allclose(r0["tiny"], oracle.lab_moments_f64(tiny), rtol=1e-7, atol=1e-6)
     assert r0["sums"][0, 0] == 37 * 52
     assert r0["range"] == (0, 6) and r1["range"] == (6, 11)
+    assert torch.equal(r0["hist"], r1["hist"]) and torch.equal(r0["hist"].long(), oracle.hist_counts(ref))   # exact integers on every rank
     clip = natural_frames(5, 6, 8, seed=9)
     assert r0["span"] == (0, 3) and r1["span"] == (3, 5)
     assert r0["prev"] is None and torch.equal(r0["next"], clip[3])          # rank 0: no predecessor, successor = rank 1's first frame

@@ -43,6 +43,11 @@ def _worker(rank, world, port, out_dir):
         launched = pkg._native.launch_count() - before
         odd = natural_frames(1, 37, 53, seed=4).to(dev)              # odd height and width: unequal row counts, scalar path
         sums_odd = d.reference_sums_distributed(odd)
+        hist = d.reference_histogram_distributed(ref)                # histogram mode: 3 x 256 counters per rank, same collective shape
+        clip = natural_frames(3 * world, 24, 32, seed=7).to(dev)     # temporal extension: one halo frame per shard boundary
+        ca, cb = d.shard_range(3 * world, rank, world)
+        prev, nxt = d.exchange_halo_frames(clip[ca:cb])
+        temporal = pkg.ops.temporal_sharpen(clip[ca:cb].contiguous(), 0.7, prev, nxt)
         tiny = natural_frames(1, 1, 8, seed=5).to(dev)               # fewer rows than ranks: a rank contributes zeros
         sums_tiny = d.reference_sums_distributed(tiny)
         # the statistics drive a sharded colour match: rank r owns frames [r*2, r*2+2) of a 2*world-frame clip
@@ -51,7 +56,7 @@ def _worker(rank, world, port, out_dir):
         chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(ref_sums=sums, strength=1.0), device=dev)
         shard_out = chain(frames[a:b].to(dev), first_frame=a)
         torch.cuda.synchronize(dev)
-        torch.save({"sums": sums.cpu(), "odd": sums_odd.cpu(), "tiny": sums_tiny.cpu(), "launched": launched, "shard": shard_out.cpu(), "range": (a, b),
+        torch.save({"sums": sums.cpu(), "odd": sums_odd.cpu(), "tiny": sums_tiny.cpu(), "launched": launched, "shard": shard_out.cpu(), "range": (a, b), "hist": hist.cpu(), "temporal": temporal.cpu(), "trange": (ca, cb),
                     "backend": dist.get_backend()}, os.path.join(out_dir, "r%d.pt" % rank))
     finally:
         dist.destroy_process_group()
@@ -81,6 +86,16 @@ def test_reference_moments_allgather_over_nccl(pkg, cuda_device, tmp_path):
         whole = pkg.ops.lab_moments(img).cpu()
         assert torch.allclose(res[0][key], whole, rtol=1e-12, atol=1e-9), key
         assert res[0][key][0, 0] == H * W
+    # histogram counts: exact integers, identical on every rank, equal to the single-GPU counts
+    img = natural_frames(1, 270, 480, seed=3).to(cuda_device)
+    for r in res:
+        assert torch.equal(r["hist"], pkg.ops.hist_counts(img).cpu())
+    # temporal sharpen over shards with exchanged halo frames == the whole clip on one GPU
+    clip = natural_frames(3 * world, 24, 32, seed=7).to(cuda_device)
+    whole_t = pkg.ops.temporal_sharpen(clip, 0.7).cpu()
+    for r in res:
+        ca, cb = r["trange"]
+        assert torch.equal(r["temporal"], whole_t[ca:cb])
     # the sharded colour match equals the single-GPU run on the whole clip
     frames = natural_frames(2 * world, 64, 96, seed=6).to(cuda_device)
     chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(ref_sums=res[0]["sums"], strength=1.0), device=cuda_device)

@@ -329,3 +329,66 @@ def test_temporal_sharpen_full_size_config5_shape(pkg, cuda_device, oracle):
     still = x[:1].repeat(6, 1, 1, 1).to(cuda_device)               # a still clip is a fixed point up to the rounding of (3x)/3
     assert maxdiff(pkg.ops.temporal_sharpen(still, 2.0), still) <= 3e-7
     assert torch.equal(pkg.ops.temporal_sharpen(x.to(cuda_device), 0.0).cpu(), x)      # strength 0 = identity
+
+
+# ------------------------------------------------------------------------------------------------------
+# histogram / CDF colour transfer — a labelled extension (the reference has no histogram; the NumPy oracle IS the specification)
+# ------------------------------------------------------------------------------------------------------
+def test_histogram_colormatch_vs_spec_oracle(pkg, cuda_device, oracle):
+    x = natural_frames(3, 72, 93, seed=80)
+    x[1] = (x[1] * 0.6 + 0.3).clamp(0, 1)
+    x[0, :2, :5] = torch.tensor([0.0, 1.0, 0.5])              # exact bin edges / extremes
+    ref = natural_frames(1, 50, 61, seed=81) * 0.8 + 0.05
+    xd, rd = x.to(cuda_device), ref.to(cuda_device)
+    counts = pkg.ops.hist_counts(xd)
+    want_counts = oracle.hist_counts(x)
+    assert torch.equal(counts.cpu().long(), want_counts)       # integers: exact
+    assert int(counts[0].sum()) == 3 * 72 * 93
+    # row shards add up to the whole image (what the ranks exchange: dist.reference_histogram_distributed)
+    parts = pkg.ops.hist_counts(rd, 0, 20) + pkg.ops.hist_counts(rd, 20, 30)
+    assert torch.equal(parts, pkg.ops.hist_counts(rd))
+    tables = pkg.ops.histmatch_tables(counts, pkg.ops.hist_counts(rd))
+    T = oracle.histmatch_tables(want_counts, oracle.hist_counts(ref))
+    assert torch.equal(tables[..., 0].cpu(), T[..., :256])     # fp64 edge arithmetic with one rounding per op: bit-identical
+    assert torch.equal(tables[..., 1].cpu(), T[..., 1:] - T[..., :256])
+    assert bool((tables[..., 1] >= 0).all())                   # monotone
+    for strength in (1.0, 0.35):
+        got = pkg.ops.histmatch_apply(xd, tables, strength, 1.0 - strength)
+        assert torch.equal(got.cpu(), oracle.hist_match(x, ref, strength))
+    # the node, host tensors in / out, chunked
+    node = pkg.NODE_CLASS_MAPPINGS["VRGDG_B200_HistogramColorMatch"]()
+    assert torch.equal(node.match_histogram(x, ref, 0.35, 2)[0], oracle.hist_match(x, ref, 0.35))
+    # 16-bit and uint8 BGR frames: fp32 arithmetic on the decoded values, one rounding / the truncating encode
+    for dt in (torch.float16, torch.bfloat16):
+        xh, rh = x.to(dt), ref.to(dt)
+        th = pkg.ops.histmatch_tables(pkg.ops.hist_counts(xh.to(cuda_device)), pkg.ops.hist_counts(rh.to(cuda_device)))
+        assert torch.equal(pkg.ops.histmatch_apply(xh.to(cuda_device), th, 1.0, 0.0).cpu(), oracle.hist_match(xh.float(), rh.float(), 1.0).to(dt))
+    u8 = (x * 255).to(torch.uint8).flip(-1).contiguous()
+    r8 = (ref * 255).to(torch.uint8).flip(-1).contiguous()
+    dec, rdec = oracle.frames_to_tensor(list(u8.numpy())), oracle.frames_to_tensor(list(r8.numpy()))
+    t8 = pkg.ops.histmatch_tables(pkg.ops.hist_counts(u8.to(cuda_device)), pkg.ops.hist_counts(r8.to(cuda_device)))
+    enc = np.stack(oracle.tensor_to_frames(oracle.hist_match(dec, rdec, 1.0)))
+    assert np.array_equal(pkg.ops.histmatch_apply(u8.to(cuda_device), t8, 1.0, 0.0).cpu().numpy(), enc)
+    # empty reference rows -> identity tables; one reference per frame
+    ident = pkg.ops.histmatch_tables(counts, torch.zeros_like(counts[:1]))
+    assert maxdiff(pkg.ops.histmatch_apply(xd, ident, 1.0, 0.0), xd.clamp(0, 1)) <= 1e-6
+    per_frame = pkg.ops.histmatch_tables(counts, counts)       # every frame matched to itself
+    assert per_frame.shape == (3, 3, 256, 2)
+
+
+def test_histogram_colormatch_full_size_properties(pkg, cuda_device):
+    """configs[2] frame size: one 4K frame matched to a 4K reference lands on the reference's CDF (size-independent property)"""
+    x = natural_frames(1, 2160, 3840, seed=82, device=cuda_device)
+    ref = (natural_frames(1, 2160, 3840, seed=83, device=cuda_device) * 0.7 + 0.2).clamp(0, 1)
+    cx, cr = pkg.ops.hist_counts(x), pkg.ops.hist_counts(ref)
+    assert int(cx.sum()) == 3 * 2160 * 3840
+    out = pkg.ops.histmatch_apply(x, pkg.ops.histmatch_tables(cx, cr), 1.0, 0.0)
+    co = pkg.ops.hist_counts(out)
+    n = 2160.0 * 3840.0
+    cdf_o, cdf_r = co.double().cumsum(-1) / n, cr.double().cumsum(-1) / n
+    assert float((cdf_o - cdf_r).abs().max()) < 0.02           # matched CDF follows the reference CDF (bin-quantisation slack)
+    # monotone: a brighter input never gets darker within a channel
+    idx = torch.argsort(x[0, :, :, 1].flatten()[:200000])
+    assert bool((out[0, :, :, 1].flatten()[:200000][idx].diff() >= -1e-6).all())
+    same = pkg.ops.histmatch_apply(x, pkg.ops.histmatch_tables(cx, cx), 1.0, 0.0)
+    assert maxdiff(same, x) <= 1e-6                            # a frame matched to itself is the identity (plateau rule of the inverse CDF)

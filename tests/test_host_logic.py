@@ -16,7 +16,7 @@ def meta():
         return json.load(fh)
 
 
-EXTRA_KEYS = {"VRGDG_B200_PostChain", "VRGDG_B200_EnhanceFrames", "VRGDG_B200_TemporalSharpen"}      # this package's own nodes (no reference counterpart)
+EXTRA_KEYS = {"VRGDG_B200_PostChain", "VRGDG_B200_EnhanceFrames", "VRGDG_B200_TemporalSharpen", "VRGDG_B200_HistogramColorMatch"}      # this package's own nodes (no reference counterpart)
 
 
 def test_node_mappings_and_api_match_reference(pkg, meta):

@@ -94,6 +94,22 @@ def rows_cm():
         torch.cuda.empty_cache()
 
 
+def rows_ext():
+    """the two labelled extensions: histogram / CDF colour match and the temporal 3-frame sharpen"""
+    for (B, H, W, dt, tag) in ((8, 2160, 3840, torch.float32, "4k_f32"), (32, 1080, 1920, torch.float32, "1080p_f32")):
+        x = natural_frames(8, H, W, seed=1, dtype=dt, device=dev).repeat(B // 8, 1, 1, 1).contiguous()
+        npix, bpp = B * H * W, 2 * 3 * x.element_size()
+        ref_counts = ops.hist_counts(natural_frames(1, H, W, seed=9, dtype=dt, device=dev))
+        report(f"hist_counts/{tag}", timeit(lambda: ops.hist_counts(x)), npix, bpp / 2)
+        counts = ops.hist_counts(x)
+        tables = ops.histmatch_tables(counts, ref_counts)
+        report(f"histmatch_apply/{tag}", timeit(lambda: ops.histmatch_apply(x, tables, 1.0, 0.0)), npix, bpp)
+        report(f"histmatch_whole/{tag}", timeit(lambda: ops.histmatch_apply(x, ops.histmatch_tables(ops.hist_counts(x), ref_counts), 1.0, 0.0)), npix, bpp)
+        report(f"temporal_sharpen/{tag}", timeit(lambda: ops.temporal_sharpen(x, 0.5)), npix, bpp)
+        del x
+        torch.cuda.empty_cache()
+
+
 def rows_chains():
     lut = lut33()
     for (B, H, W, dt, tag) in ((4, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float16, "1080p_f16")):
@@ -142,3 +158,5 @@ if __name__ == "__main__":
         rows_chains()
     if "luts" in want:
         rows_luts()
+    if "ext" in want:
+        rows_ext()
