@@ -143,6 +143,19 @@ def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
         assert np.abs(out - flat(c["out_t60"][b])).max() <= 1e-5
 
 
+def test_refined_powers_accuracy(hostcheck):
+    """x^2.4, x^(1/3) of the colour match's input side: MUFU-style seed (perturbed by 3e-7 in the host build) + one division-free
+    Newton step on the inverse root must land within a few fp32 roundings of the true power"""
+    hostcheck.hc_pows.argtypes = [vp, vp, vp, vp, i64]
+    x = np.exp(np.linspace(np.log(0.008856), np.log(2.0), 200001)).astype(np.float32)
+    p24, pinv, cb = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+    hostcheck.hc_pows(P(x), P(p24), P(pinv), P(cb), x.shape[0])
+    x64 = x.astype(np.float64)
+    assert np.abs(cb / np.cbrt(x64) - 1.0).max() < 4e-7
+    assert np.abs(p24 / x64 ** 2.4 - 1.0).max() < 8e-7                       # (x * x^-0.2)^3: three times the error of the refined root
+    assert np.abs(pinv / x64 ** (1.0 / 2.4) - 1.0).max() < 8e-7
+
+
 def test_fspace_moments_equal_lab_moments(hostcheck, oracle):
     """the moments kernel sums (fy, fx-fy, fy-fz) and converts to Lab sums in fp64 (csrc/vrgdg_math.cuh::cm_sums_to_lab_host)"""
     hostcheck.hc_lab_sums.argtypes = [vp, i64, vp]
