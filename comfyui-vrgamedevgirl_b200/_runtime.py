@@ -37,6 +37,20 @@ def result_device(images, numpy_path=False):
 _SIDE_STREAMS = {}
 
 
+def _pin_result(src, nbytes):
+    """Host results are allocated pinned when the source is pinned, or when they are small enough (VRGDG_PIN_RESULT_BYTES, default
+    2 GiB): the download then runs at PCIe speed instead of through the driver's pageable bounce buffer, and the next node's upload of
+    that tensor does too.  torch caches freed pinned blocks, so repeated runs of a workflow do not pay cudaHostAlloc again."""
+    import os
+    if src.is_pinned():
+        return True
+    try:
+        limit = int(os.environ.get("VRGDG_PIN_RESULT_BYTES", str(2 << 30)))
+    except ValueError:
+        limit = 2 << 30
+    return 0 < nbytes <= limit
+
+
 def _side_streams(dev):
     """(upload, download) streams of a device, created once (stream creation is not free and ComfyUI calls nodes repeatedly)."""
     key = (dev.type, dev.index)
@@ -82,9 +96,12 @@ def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
         if chunk >= B:
             res = fn(src, 0)
             return res if res.device == out_device else res.to(out_device)
-        res = torch.empty(src.shape, dtype=src.dtype, device=out_device)
+        to_host = out_device.type == "cpu"
+        res = torch.empty(src.shape, dtype=src.dtype, device=out_device, pin_memory=to_host and _pin_result(src, src.numel() * src.element_size()))
         for i in range(0, B, chunk):
-            res[i:i + chunk].copy_(fn(src[i:i + chunk], i))
+            res[i:i + chunk].copy_(fn(src[i:i + chunk], i), non_blocking=to_host)
+        if to_host:
+            torch.cuda.current_stream(src.device).synchronize()
         return res
     dev = device if device is not None else compute_device()
     if B == 0:
@@ -95,7 +112,8 @@ def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
         compute = torch.cuda.current_stream(dev)
         up, down = _side_streams(dev)
         if out is None:
-            out = torch.empty(src.shape, dtype=src.dtype, pin_memory=src.is_pinned()) if to_cpu else torch.empty(src.shape, dtype=src.dtype, device=out_device)
+            out = torch.empty(src.shape, dtype=src.dtype, pin_memory=_pin_result(src, src.numel() * src.element_size())) if to_cpu \
+                else torch.empty(src.shape, dtype=src.dtype, device=out_device)
         elif out.shape != src.shape or out.dtype != src.dtype or out.device != out_device:
             raise ValueError("vrgdg_b200: `out` must match the source frames in shape and dtype and live on %s" % out_device)
         n_chunks = (B + chunk - 1) // chunk
