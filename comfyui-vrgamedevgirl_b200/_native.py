@@ -23,6 +23,7 @@ BORDER_REPLICATE, BORDER_ZERO = 0, 1
 SEED_PER_CLIP, SEED_PER_FRAME = 0, 1
 CHAIN_FAST_MATH = 1
 CHAIN_CM_RECOMPUTE = 2
+CHAIN_CM_SERIAL = 4
 
 
 class ChainDesc(ctypes.Structure):

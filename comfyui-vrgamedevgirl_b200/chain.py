@@ -29,7 +29,7 @@ class PostChain:
         self.timing = None          # set to a list to collect (moments_start, moments_end, apply_start, apply_end) CUDA events per call
         # colour-match schedule (vrgdg_chain_cm_apply): one library call; `split` = the three-call path (statistics, parameters,
         # apply as separate entry points; what `timing` needs), `recompute` / `group_frames`: see include/vrgdg_b200.h
-        self.split, self.recompute, self.group_frames = False, False, 0
+        self.split, self.recompute, self.group_frames, self.serial = False, False, 0, False
         self._scratch = None
         if lut is not None:
             self._lut_dev = ops.pack_lut(lut["lut_data"]["lut"], self.device)
@@ -106,7 +106,7 @@ class PostChain:
         if self.colormatch is not None and not self.split and self.timing is None:
             d = self._desc(frames, first_frame, keep, ext_noise, fused_cm=True)
             res, self._scratch = ops.chain_cm_apply(frames, d, self._ref_sums, ext_noise=ext_noise, out=out, fast_math=fast_math,
-                                                    recompute=self.recompute, group_frames=self.group_frames, scratch=self._scratch)
+                                                    recompute=self.recompute, group_frames=self.group_frames, scratch=self._scratch, serial=self.serial)
             return res
         d = self._desc(frames, first_frame, keep, ext_noise)
         if self.timing is None:

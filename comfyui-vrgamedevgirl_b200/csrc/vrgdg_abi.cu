@@ -386,7 +386,8 @@ static int chain_point_params(const vrgdg_chain_desc* d, int B, int H, int W, Po
  * frames) and the grain + forward-Lab half of the colour match has already happened: stages become ST_CMF [| ST_LUT].
  * cm_params (when non-null) replaces desc->cm_params; frame_offset is added to both grain frame indices (group scheduling). */
 static int chain_apply_core(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* d,
-                            const void* ext_noise, bool fast, void* stream, const float* cm_params, bool from_f, int64_t frame_offset) {
+                            const void* ext_noise, bool fast, void* stream, const float* cm_params, bool from_f, int64_t frame_offset,
+                            int grid_limit = 0) {
   if (!d) return fail(VRGDG_E_INVALID, "vrgdg_chain_apply: null descriptor");
   int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_apply");
   if (rc) return rc;
@@ -398,6 +399,7 @@ static int chain_apply_core(const void* in, void* out, int B, int H, int W, int 
   if ((rc = get_ctx(stream, ctx))) return rc;
   TileParams Q;
   memset(&Q, 0, sizeof(Q));
+  Q.grid_limit = grid_limit;
   int mask = 0;
   bool exact = true;
   vrgdg_chain_desc dd = *d;
@@ -480,13 +482,15 @@ int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, int dtype, 
 }
 
 /* ---- one call for a chain WITH colour match ------------------------------------------------------------------------------
- * scratch layout: [sums B x 7 doubles][params B x 12 floats, padded to 16 bytes][partials G x 296 x 6 doubles][f-planes G x H x W x 3 floats] */
+ * scratch layout: [sums B x 7 doubles][params B x 12 floats, padded to 16 bytes][partials NB x G x 592 x 6 doubles]
+ *                 [f-planes NB x G x H x W x 3 floats], NB = 2 buffers when the pipelined schedule can run (fp32 frames, more than
+ *                 one group), else 1. */
 static int cm_group_frames(int B, int H, int W, int dtype, int flags, int group_frames) {
   (void)dtype; (void)flags;
   if (group_frames > 0) return group_frames < B ? group_frames : (B > 0 ? B : 1);
   // Measured (profiles/README.md, round 2): both passes are instruction-issue bound, so keeping a group's re-read set inside L2
   // (1-2 frames per group) buys nothing, while short launches lose 5-20 % to their last partial wave of tiles.  Default = about
-  // 64 Mpixel per group (8 x 4K, 32 x 1080p): > 25 000 tiles per launch, <= 800 MB of f-planes.
+  // 64 Mpixel per group (8 x 4K, 32 x 1080p): > 25 000 tiles per launch, <= 800 MB of f-planes per buffer.
   const int64_t px = (int64_t)H * W;
   int64_t g = px > 0 ? (((int64_t)64 << 20) + px - 1) / px : 1;
   if (g < 1) g = 1;
@@ -494,18 +498,44 @@ static int cm_group_frames(int B, int H, int W, int dtype, int flags, int group_
   return g < B ? (int)g : (B > 0 ? B : 1);
 }
 
+static bool cm_wants_planes(int dtype, int flags) { return dtype == VRGDG_F32 && !(flags & VRGDG_CHAIN_CM_RECOMPUTE); }
 static bool cm_uses_planes(int dtype, int H, int W, const void* in, int flags) {
-  return dtype == VRGDG_F32 && !(flags & VRGDG_CHAIN_CM_RECOMPUTE) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+  (void)H;
+  return cm_wants_planes(dtype, flags) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+}
+static int cm_buffers(int B, int G, int dtype, int flags) {
+  return (cm_wants_planes(dtype, flags) && !(flags & VRGDG_CHAIN_CM_SERIAL) && B > G) ? 2 : 1;
 }
 
 int64_t vrgdg_chain_cm_scratch_bytes(int B, int H, int W, int dtype, int flags, int group_frames) {
   if (B < 0 || H < 0 || W < 0 || !dtype_ok(dtype)) return 0;
   const int g = cm_group_frames(B, H, W, dtype, flags, group_frames);
+  const int nb = cm_buffers(B, g, dtype, flags);
   int64_t n = (int64_t)B * 7 * 8;
   n += (((int64_t)B * 12 * 4 + 15) / 16) * 16;
-  n += (int64_t)g * MOMENT_BLOCKS * 6 * 8;
-  if (dtype == VRGDG_F32 && !(flags & VRGDG_CHAIN_CM_RECOMPUTE)) n += (int64_t)g * H * W * 3 * 4;
-  return n + 256;
+  n += (int64_t)nb * g * MOMENT_BLOCKS * 6 * 8;
+  if (cm_wants_planes(dtype, flags)) n += (int64_t)nb * ((((int64_t)g * H * W * 3 * 4) + 255) / 256) * 256;
+  return n + 512;
+}
+
+/* Side streams of the pipelined schedule: one high- and one low-priority non-blocking stream per (thread, device), created on first
+ * use and kept for the life of the thread (the library owns no other CUDA resources). */
+struct CmStreams { cudaStream_t hi = nullptr, lo = nullptr; };
+static int cm_streams(CmStreams*& out) {
+  static thread_local CmStreams per_dev[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+  if (dev < 0 || dev >= 64) return fail(VRGDG_E_UNSUPPORTED, "device index %d", dev);
+  CmStreams& s = per_dev[dev];
+  if (!s.hi) {
+    int least = 0, greatest = 0;
+    if ((e = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return fail_cuda(e, "cudaDeviceGetStreamPriorityRange");
+    if ((e = cudaStreamCreateWithPriority(&s.hi, cudaStreamNonBlocking, greatest)) != cudaSuccess) return fail_cuda(e, "cudaStreamCreateWithPriority");
+    if ((e = cudaStreamCreateWithPriority(&s.lo, cudaStreamNonBlocking, least)) != cudaSuccess) return fail_cuda(e, "cudaStreamCreateWithPriority");
+  }
+  out = &s;
+  return VRGDG_OK;
 }
 
 int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
@@ -516,6 +546,8 @@ int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dty
   int rc = check_frames(in, out, B, H, W, dtype, "vrgdg_chain_cm_apply");
   if (rc) return rc;
   if (n_ref != 1 && n_ref != B) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: reference batch %d is neither 1 nor %d", n_ref, B);
+  if (desc->grain_enabled && desc->grain_seed_mode != VRGDG_SEED_PER_CLIP && desc->grain_seed_mode != VRGDG_SEED_PER_FRAME)
+    return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: bad grain seed_mode %d", desc->grain_seed_mode);
   if ((int64_t)B * H * W == 0) return VRGDG_OK;
   if (!ref_sums || !scratch) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: null pointer");
   if (in == out) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply cannot run in place");
@@ -527,46 +559,101 @@ int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dty
   if ((rc = get_ctx(stream, ctx))) return rc;
   const int G = cm_group_frames(B, H, W, dtype, flags, group_frames);
   const bool planes = cm_uses_planes(dtype, H, W, in, flags);
+  const int NB = cm_buffers(B, G, dtype, flags);
+  const bool piped = planes && NB == 2;                 // statistics pass of group g+1 overlaps the apply pass of group g
   char* sp = reinterpret_cast<char*>(scratch);
   double* sums = reinterpret_cast<double*>(sp);
   sp += (int64_t)B * 7 * 8;
   float* params = reinterpret_cast<float*>(sp);
   sp += (((int64_t)B * 12 * 4 + 15) / 16) * 16;
-  double* partials = reinterpret_cast<double*>(sp);
+  double* partials[2] = {reinterpret_cast<double*>(sp), nullptr};
   sp += (int64_t)G * MOMENT_BLOCKS * 6 * 8;
+  if (NB == 2) { partials[1] = reinterpret_cast<double*>(sp); sp += (int64_t)G * MOMENT_BLOCKS * 6 * 8; }
   sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(sp) + 255u) & ~(uintptr_t)255u);
-  float* fplanes = planes ? reinterpret_cast<float*>(sp) : nullptr;
+  const int64_t plane_bytes = ((((int64_t)G * H * W * 3 * 4) + 255) / 256) * 256;
+  float* fplanes[2] = {planes ? reinterpret_cast<float*>(sp) : nullptr, (planes && NB == 2) ? reinterpret_cast<float*>(sp + plane_bytes) : nullptr};
   const size_t es = elem_size(dtype);
   const size_t frame_bytes = (size_t)H * W * 3 * es;
   const size_t noise_es = (dtype == VRGDG_U8BGR) ? 4 : es;
   const bool fast = (flags & VRGDG_CHAIN_FAST_MATH) != 0;
-  for (int g0 = 0; g0 < B; g0 += G) {
+  const int ngroups = (B + G - 1) / G;
+
+  // Pipelined schedule (fp32 frames, several groups): the statistics pass (instruction-issue / XU bound, 128-thread blocks of 8 K
+  // registers) of group g+1 runs on a low-priority side stream WHILE the apply pass (L1 data-pipe bound, two resident tile CTAs per
+  // SM that leave exactly that much of the register file) of group g runs on a high-priority one; f-planes and partials are double
+  // buffered; events fork the side streams from the caller's stream and join them back, so the call stays stream-ordered.
+  // Tile CTAs of the apply pass while a statistics pass runs beside it: every tile CTA less frees registers for 3.5 more 128-thread
+  // statistics blocks.  Default from the sweep in profiles/README.md; VRGDG_PIPE_TILE_CTAS overrides (tuning only).
+  int tile_ctas = 0;
+  if (piped) {
+    const char* ev = getenv("VRGDG_PIPE_TILE_CTAS");
+    tile_ctas = ev ? atoi(ev) : 0;
+  }
+  CmStreams* ss = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr};
+  LaunchCtx lo = ctx, hi = ctx;
+  if (piped) {
+    if ((rc = cm_streams(ss))) return rc;
+    lo.stream = ss->lo; hi.stream = ss->hi;
+    cudaError_t e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&ev_p1[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_p2[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ev_start, ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lo.stream, ev_start, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hi.stream, ev_start, 0);
+    if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (events)");
+  }
+  auto cleanup = [&]() {
+    if (ev_start) cudaEventDestroy(ev_start);
+    for (int i = 0; i < 2; ++i) { if (ev_p1[i]) cudaEventDestroy(ev_p1[i]); if (ev_p2[i]) cudaEventDestroy(ev_p2[i]); }
+  };
+
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int g0 = gi * G, buf = piped ? (gi & 1) : 0;
     const int n = (B - g0 < G) ? B - g0 : G;
     const char* gin = reinterpret_cast<const char*>(in) + (size_t)g0 * frame_bytes;
     char* gout = reinterpret_cast<char*>(out) + (size_t)g0 * frame_bytes;
     const void* gnoise = ext_noise ? reinterpret_cast<const char*>(ext_noise) + (size_t)g0 * H * W * 3 * noise_es : nullptr;
+    const LaunchCtx& c1 = piped ? lo : ctx;
+    cudaError_t e = cudaSuccess;
+    if (piped && gi >= 2) e = cudaStreamWaitEvent(lo.stream, ev_p2[buf], 0);      // the apply pass of group gi-2 has released this buffer
+    if (e != cudaSuccess) { cleanup(); return fail_cuda(e, "vrgdg_chain_cm_apply (wait)"); }
     // pass 1: grain (recomputed from the counter-based generator or read from ext_noise) -> Lab statistics [+ f-planes]
     PointParams P;
     zero_point(P, n, H, W);
     if (desc->grain_enabled) {
-      if (desc->grain_seed_mode != VRGDG_SEED_PER_CLIP && desc->grain_seed_mode != VRGDG_SEED_PER_FRAME) return fail(VRGDG_E_INVALID, "vrgdg_chain_cm_apply: bad grain seed_mode %d", desc->grain_seed_mode);
       P.gI = desc->grain_intensity; P.gs = desc->grain_sat; P.goms = desc->grain_one_minus_sat;
       P.seed = desc->grain_seed; P.frame0 = desc->grain_frame0 + g0; P.seed_mode = desc->grain_seed_mode;
       grain_make_key(P.seed, P.seed_mode, P.gkey);
       P.ext_noise = gnoise;
     }
-#define MO(T) launch_moments<T>(gin, P, desc->grain_enabled != 0, 0, H, sums + (int64_t)g0 * 7, partials, ctx, fplanes)
-    cudaError_t e = DISPATCH_DTYPE(dtype, MO);
+#define MO(T) launch_moments<T>(gin, P, desc->grain_enabled != 0, 0, H, sums + (int64_t)g0 * 7, partials[buf], c1, fplanes[buf], piped)
+    e = DISPATCH_DTYPE(dtype, MO);
 #undef MO
-    if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (moments)");
-    k_colormatch_params<<<(n + 127) / 128, 128, 0, ctx.stream>>>(sums + (int64_t)g0 * 7, n, ref_sums + (n_ref == 1 ? 0 : (int64_t)g0 * 7), n_ref == 1 ? 1 : n,
-                                                                params + (int64_t)g0 * 12);
+    if (e != cudaSuccess) { cleanup(); return fail_cuda(e, "vrgdg_chain_cm_apply (moments)"); }
+    k_colormatch_params<<<(n + 127) / 128, 128, 0, c1.stream>>>(sums + (int64_t)g0 * 7, n, ref_sums + (n_ref == 1 ? 0 : (int64_t)g0 * 7), n_ref == 1 ? 1 : n,
+                                                               params + (int64_t)g0 * 12);
     count_launch();
-    if ((e = cudaGetLastError()) != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (params)");
+    if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return fail_cuda(e, "vrgdg_chain_cm_apply (params)"); }
+    if (piped) {
+      if ((e = cudaEventRecord(ev_p1[buf], lo.stream)) == cudaSuccess) e = cudaStreamWaitEvent(hi.stream, ev_p1[buf], 0);
+      if (e != cudaSuccess) { cleanup(); return fail_cuda(e, "vrgdg_chain_cm_apply (record)"); }
+    }
     // pass 2: the fused apply, from the f-planes (no grain, no forward Lab) or from the frames
-    rc = chain_apply_core(planes ? reinterpret_cast<const void*>(fplanes) : reinterpret_cast<const void*>(gin), gout, n, H, W, dtype, desc, gnoise, fast,
-                          stream, params + (int64_t)g0 * 12, planes, g0);
-    if (rc) return rc;
+    rc = chain_apply_core(planes ? reinterpret_cast<const void*>(fplanes[buf]) : reinterpret_cast<const void*>(gin), gout, n, H, W, dtype, desc, gnoise, fast,
+                          piped ? reinterpret_cast<void*>(hi.stream) : stream, params + (int64_t)g0 * 12, planes, g0, piped ? tile_ctas : 0);
+    if (rc) { cleanup(); return rc; }
+    if (piped) {
+      if ((e = cudaEventRecord(ev_p2[buf], hi.stream)) != cudaSuccess) { cleanup(); return fail_cuda(e, "vrgdg_chain_cm_apply (record)"); }
+    }
+  }
+  if (piped) {   // join: the caller's stream continues after the last apply pass (which follows every statistics pass)
+    cudaError_t e = cudaStreamWaitEvent(ctx.stream, ev_p2[(ngroups - 1) & 1], 0);
+    if (e == cudaSuccess && ngroups >= 2) e = cudaStreamWaitEvent(ctx.stream, ev_p2[(ngroups - 2) & 1], 0);
+    cleanup();
+    if (e != cudaSuccess) return fail_cuda(e, "vrgdg_chain_cm_apply (join)");
   }
   return VRGDG_OK;
 }

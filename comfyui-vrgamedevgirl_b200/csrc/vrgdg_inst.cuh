@@ -104,7 +104,8 @@ static cudaError_t launch_tile_k(const CUtensorMap* tmap, const void* in, void* 
   if (MASK & ST_LUT) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * TileCfg<T, MASK>::MINB * 100 / (228 * 1024)) + 1);
   static int occ = occupancy_of(kern, NT, smem);
   if (Q.total_tiles == 0) return cudaSuccess;
-  const int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx.sms * occ);
+  int grid = (int)std::min<int64_t>(Q.total_tiles, (int64_t)ctx.sms * occ);
+  if (Q.grid_limit > 0 && grid > Q.grid_limit) grid = Q.grid_limit;
   CUtensorMap dummy;
   if (!tmap) { memset(&dummy, 0, sizeof(dummy)); tmap = &dummy; }
   kern<<<grid, NT, smem, ctx.stream>>>(*tmap, reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out), Q);
@@ -139,25 +140,36 @@ cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, Tile
 }
 
 // ---- moments -------------------------------------------------------------------------------------
+template <typename T, bool GRAIN, bool VEC, int NT>
+static cudaError_t launch_moments_k(const T* src, const PointParams& P, int row0, int rows, double* partials, float* fplanes, const LaunchCtx& ctx) {
+  auto kern = k_lab_moments<T, GRAIN, VEC, NT>;
+  if (NT == MOMENT_UNIT) {
+    // pipelined schedule: these blocks share SMs with two resident k_tile CTAs, whose shared-memory carve-out they must not fight
+    // (an SM changes its carve-out only when idle, which would serialise the two kernels)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 64);
+  }
+  dim3 grid(MOMENT_BLOCKS / (NT / MOMENT_UNIT), P.B);
+  kern<<<grid, NT, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows, double* sums,
-                           double* partials, const LaunchCtx& ctx, float* fplanes) {
+                           double* partials, const LaunchCtx& ctx, float* fplanes, bool small_blocks) {
   if (P.B == 0) return cudaSuccess;
   typedef typename Io<T>::word_t word_t;
   constexpr int PX = (int)(sizeof(word_t) / sizeof(T));
   const bool vec = (P.W % PX == 0) && ((reinterpret_cast<uintptr_t>(in) & (sizeof(word_t) - 1)) == 0);
   if (fplanes && !(vec && sizeof(T) == 4 && aligned16(fplanes))) return cudaErrorInvalidValue;   // the ABI layer only asks for planes when this holds
-  dim3 grid(MOMENT_BLOCKS, P.B);
   const T* src = reinterpret_cast<const T*>(in);
-  if (grain) {
-    if (vec) k_lab_moments<T, true, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
-    else k_lab_moments<T, true, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
-  } else {
-    if (vec) k_lab_moments<T, false, true><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
-    else k_lab_moments<T, false, false><<<grid, 256, 0, ctx.stream>>>(src, P, row0, rows, partials, fplanes);
-  }
-  count_launch();
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (small_blocks && vec && grain) e = launch_moments_k<T, true, true, MOMENT_UNIT>(src, P, row0, rows, partials, fplanes, ctx);
+  else if (small_blocks && vec) e = launch_moments_k<T, false, true, MOMENT_UNIT>(src, P, row0, rows, partials, fplanes, ctx);
+  else if (grain && vec) e = launch_moments_k<T, true, true, 256>(src, P, row0, rows, partials, fplanes, ctx);
+  else if (grain) e = launch_moments_k<T, true, false, 256>(src, P, row0, rows, partials, fplanes, ctx);
+  else if (vec) e = launch_moments_k<T, false, true, 256>(src, P, row0, rows, partials, fplanes, ctx);
+  else e = launch_moments_k<T, false, false, 256>(src, P, row0, rows, partials, fplanes, ctx);
   if (e != cudaSuccess) return e;
   k_moments_final<<<P.B, 32, 0, ctx.stream>>>(partials, MOMENT_BLOCKS, (double)rows * (double)P.W, sums);
   count_launch();
@@ -186,7 +198,7 @@ cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const Laun
   template cudaError_t launch_point<T>(const void*, void*, const PointParams&, int, bool, const LaunchCtx&);              \
   template cudaError_t launch_lut_rgba<T>(const void*, void*, int64_t, const LutParams&, const LaunchCtx&);               \
   template cudaError_t launch_tile<T>(const CUtensorMap*, const void*, void*, TileParams&, int, bool, const LaunchCtx&);  \
-  template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&, float*); \
+  template cudaError_t launch_moments<T>(const void*, const PointParams&, bool, int, int, double*, double*, const LaunchCtx&, float*, bool); \
   template cudaError_t launch_adjust<T>(const void*, void*, const AdjustParams&, int, float*, float*, const LaunchCtx&);              \
   template cudaError_t launch_resize<T>(const void*, void*, const ResizeParams&, const LaunchCtx&);                       \
   template cudaError_t launch_blend<T>(const void*, const void*, void*, int64_t, float, float, const LaunchCtx&);         \

@@ -320,6 +320,7 @@ struct TileParams {
   int exact_stencil;            // 1: reference evaluation order, one rounding per op (bit-exact NumPy-path results for fp32)
   int use_tma;                  // 0: cooperative bounds-checked loads (any alignment)
   int vec_store;                // rows 16-byte aligned -> 16-byte stores
+  int grid_limit;               // > 0: launch at most this many persistent CTAs (pipelined colour-match schedule leaves room for the statistics pass)
 };
 
 // HEAVY = the LUT gather runs in the pre-stage.  Measured on the fused grain + LUT + unsharp chain (fp16 1080p, profiles/README.md):
@@ -805,7 +806,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
 // LAB moments: per frame {S_L,S_a,S_b,S_LL,S_aa,S_bb} in fp64, fixed reduction order (deterministic).
 // grid = (NB, B); each block writes one partial; k_moments_final folds the NB partials per frame.
 // =====================================================================================================
-constexpr int MOMENT_BLOCKS = 296;   // per frame, independent of B so results do not depend on sharding
+// Partial sums per frame: 592 reduction units of 128 threads each, independent of B (results do not depend on sharding) and of the
+// block size the kernel is launched with (a 256-thread block is two units), so every schedule produces bit-identical statistics.
+constexpr int MOMENT_BLOCKS = 592;
+constexpr int MOMENT_UNIT = 128;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -827,9 +831,14 @@ __device__ __forceinline__ void moments_add(float& r, float& g, float& b, float*
 // pixels' sums are formed in fp32 (<= 8 terms) and then added to the thread's fp64 accumulators.  !VEC: one pixel per iteration.
 // fplanes != null (fp32 frames, VEC): the pass also stores (fx, fy, fz) of every pixel, [B][H][W][3] fp32 like the frames, for the
 // ST_CMF second pass.
-template <typename T, bool GRAIN, bool VEC>
-__global__ void __launch_bounds__(256)
+// NT = 256 (two reduction units per block) or 128 (one: small enough to share an SM with two resident tile CTAs, see
+// vrgdg_chain_cm_apply's pipelined schedule).
+template <typename T, bool GRAIN, bool VEC, int NT>
+__global__ void __launch_bounds__(NT)
 k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials, float* __restrict__ fplanes) {
+  static_assert(NT % MOMENT_UNIT == 0, "whole reduction units per block");
+  constexpr int UPB = NT / MOMENT_UNIT;                       // units per block
+  const int unit = blockIdx.x * UPB + (threadIdx.x / MOMENT_UNIT), ut = threadIdx.x % MOMENT_UNIT;
   typedef typename Io<T>::word_t word_t;
   typedef typename Io<T>::noise_t noise_t;
   constexpr bool BGR = Io<T>::BGR;
@@ -843,7 +852,7 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
   const CmFold nocm = {};
   double acc[6] = {0, 0, 0, 0, 0, 0};
   const int64_t groups = (n + PX - 1) / PX;      // VEC: n % PX == 0 (host-checked)
-  for (int64_t gi = (int64_t)blockIdx.x * 256 + threadIdx.x; gi < groups; gi += (int64_t)gridDim.x * 256) {
+  for (int64_t gi = (int64_t)unit * MOMENT_UNIT + ut; gi < groups; gi += (int64_t)MOMENT_BLOCKS * MOMENT_UNIT) {
     const int64_t pif = pbeg + gi * PX;
     float v[NE], nz[NE];
     union { word_t q[3]; T e[NE]; } u;
@@ -896,7 +905,7 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
       }
     }
   }
-  __shared__ double red[8][6];
+  __shared__ double red[NT / 32][6];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -904,11 +913,12 @@ k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, doubl
     if (lane == 0) red[wid][q] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
+  if (ut < 6) {                                               // one partial per 128-thread unit: its four warps in order
+    const int w0 = (threadIdx.x / MOMENT_UNIT) * (MOMENT_UNIT / 32);
     double v = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    partials[((int64_t)frame * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+    for (int w = 0; w < MOMENT_UNIT / 32; ++w) v += red[w0 + w][ut];
+    partials[((int64_t)frame * MOMENT_BLOCKS + unit) * 6 + ut] = v;
   }
 }
 
@@ -1013,7 +1023,8 @@ template <typename T> cudaError_t launch_lut_rgba(const void* in, void* out, int
 template <typename T> cudaError_t launch_tile(const CUtensorMap* tmap, const void* in, void* out, TileParams& Q, int mask,
                                               bool exact, const LaunchCtx& ctx);
 template <typename T> cudaError_t launch_moments(const void* in, const PointParams& P, bool grain, int row0, int rows,
-                                                 double* sums, double* partials, const LaunchCtx& ctx, float* fplanes = nullptr);
+                                                 double* sums, double* partials, const LaunchCtx& ctx, float* fplanes = nullptr,
+                                                 bool small_blocks = false);
 template <typename T> cudaError_t launch_u8_in(const uint8_t* in, void* out, int64_t npix, const LaunchCtx& ctx);
 template <typename T> cudaError_t launch_u8_out(const void* in, uint8_t* out, int64_t npix, const LaunchCtx& ctx);
 template <typename T> void tile_geometry(int H, int RW, int& tiles_x, int& tiles_y, int& box_x, int& box_y);

@@ -184,6 +184,10 @@ def chain_apply(images, desc, ext_noise=None, keepalive=(), out=None, fast_math=
     return out
 
 
+def _cm_flags(fast_math=False, recompute=False, serial=False):
+    return (nv.CHAIN_FAST_MATH if fast_math else 0) | (nv.CHAIN_CM_RECOMPUTE if recompute else 0) | (nv.CHAIN_CM_SERIAL if serial else 0)
+
+
 def chain_cm_scratch(images, recompute=False, group_frames=0):
     """Device scratch for chain_cm_apply on frames like `images` (reusable across calls with the same shape)."""
     t = _frames(images)
@@ -193,14 +197,15 @@ def chain_cm_scratch(images, recompute=False, group_frames=0):
     return torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=t.device)
 
 
-def chain_cm_apply(images, desc, ref_sums, ext_noise=None, out=None, fast_math=False, recompute=False, group_frames=0, scratch=None):
+def chain_cm_apply(images, desc, ref_sums, ext_noise=None, out=None, fast_math=False, recompute=False, group_frames=0, scratch=None,
+                   serial=False):
     """A chain with colour match in ONE library call (vrgdg_chain_cm_apply): statistics, parameters and the fused apply, group by
     group.  desc.colormatch_enabled / cm_t / cm_one_minus_t must be set; ref_sums: [1|B,7] float64 from lab_moments."""
     t = _frames(images)
     B, H, W, _ = t.shape
     out = torch.empty_like(t) if out is None else _check_out(out, t)
     rs = ref_sums.to(device=t.device, dtype=torch.float64).reshape(-1, 7).contiguous()
-    flags = (nv.CHAIN_FAST_MATH if fast_math else 0) | (nv.CHAIN_CM_RECOMPUTE if recompute else 0)
+    flags = _cm_flags(fast_math, recompute, serial)
     lib = nv.load_library()
     need = int(lib.vrgdg_chain_cm_scratch_bytes(B, H, W, nv.DTYPE_CODE[t.dtype], flags, int(group_frames)))
     if scratch is None or scratch.numel() * scratch.element_size() < need or scratch.device != t.device:

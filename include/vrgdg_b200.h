@@ -207,6 +207,11 @@ VRGDG_API int vrgdg_chain_lab_moments_ext(const void* in, int B, int H, int W, i
  * ext_noise / flags & VRGDG_CHAIN_FAST_MATH: as vrgdg_chain_apply_ext.  scratch: vrgdg_chain_cm_scratch_bytes() bytes of device
  * memory, 256-byte aligned, owned by the caller (contents undefined afterwards).  Must not run in place. */
 #define VRGDG_CHAIN_CM_RECOMPUTE 2
+/* VRGDG_CHAIN_CM_SERIAL: run the groups one after the other on the caller's stream.  Default for fp32 frames with more than one group:
+ * the statistics pass of group g+1 overlaps the apply pass of group g (they saturate different pipes: instruction issue / XU vs the
+ * L1 data pipe) on two internal side streams forked from and joined back to the caller's stream by events; f-planes double buffered.
+ * Results are bit-identical either way. */
+#define VRGDG_CHAIN_CM_SERIAL 4
 VRGDG_API int64_t vrgdg_chain_cm_scratch_bytes(int B, int H, int W, int dtype, int flags, int group_frames);
 VRGDG_API int vrgdg_chain_cm_apply(const void* in, void* out, int B, int H, int W, int dtype, const vrgdg_chain_desc* desc,
                          const double* ref_sums, int n_ref, const void* ext_noise, int flags,

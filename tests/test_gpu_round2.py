@@ -153,6 +153,8 @@ def test_one_call_colormatch_chain_schedules_agree(pkg, cuda_device):
             c = mk()
             c.group_frames = g
             assert torch.equal(c(x, first_frame=7), fused), (dt, g)              # group size never changes a pixel
+            c.serial = True                                                      # groups one after the other instead of pipelined
+            assert torch.equal(c(x, first_frame=7), fused), (dt, g, "serial")
         # shard invariance through the one-call path
         assert torch.equal(mk()(x[2:].contiguous(), first_frame=9), fused[2:])
     # colour match without LUT / stencil (streaming second pass) and one reference per frame (n_ref == B)
@@ -170,6 +172,32 @@ def test_one_call_colormatch_chain_schedules_agree(pkg, cuda_device):
         pkg.ops.chain_cm_apply(x, nv.ChainDesc(), ref_sums)                      # no colour-match stage in the descriptor
     with pytest.raises(ValueError):
         pkg.ops.chain_cm_apply(x, d, ref_sums[:3])                               # reference batch neither 1 nor B
+
+
+def test_pipelined_colormatch_schedule_many_groups(pkg, cuda_device):
+    """the two-stream schedule (statistics pass of group g+1 under the apply pass of group g, double-buffered f-planes) on enough
+    groups to wrap the buffers several times, back to back on the caller's stream, against the serial schedule"""
+    nv = pkg._native
+    x = natural_frames(11, 136, 248, seed=30, device=cuda_device)
+    ref = natural_frames(1, 60, 80, seed=31, device=cuda_device)
+    mk = lambda: pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=42), colormatch=dict(reference_image=ref, strength=1.0),
+                                     lut=dict(lut_data=_lut33(pkg), strength=10.0), stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5), device=cuda_device)
+    serial = mk()
+    serial.group_frames, serial.serial = 2, True
+    want = serial(x, first_frame=3)
+    piped = mk()
+    piped.group_frames = 2                                      # 6 groups: buffers wrap three times
+    outs = [piped(x, first_frame=3) for _ in range(4)]          # consecutive calls reuse the scratch: ordering through the caller's stream
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, want)
+    # work queued on the caller's stream AFTER the call sees the finished frames (join), on a non-default stream too
+    side = torch.cuda.Stream(cuda_device)
+    with torch.cuda.stream(side):
+        o = piped(x, first_frame=3)
+        total = o.double().sum()
+    side.synchronize()
+    assert float(total) == float(want.double().sum())
 
 
 def test_moments_vector_and_scalar_paths_agree(pkg, cuda_device, oracle):

@@ -55,8 +55,8 @@ def lut33():
 
 def rows_cm():
     lut = lut33()
-    for (B, H, W, dt, tag) in ((8, 2160, 3840, torch.float32, "4k_f32"), (16, 1080, 1920, torch.float32, "1080p_f32"), (8, 2160, 3840, torch.float16, "4k_f16")):
-        x = natural_frames(B, H, W, seed=1, dtype=dt, device=dev)
+    for (B, H, W, dt, tag) in ((32, 2160, 3840, torch.float32, "4k_f32"), (64, 1080, 1920, torch.float32, "1080p_f32"), (8, 2160, 3840, torch.float16, "4k_f16")):
+        x = natural_frames(8, H, W, seed=1, dtype=dt, device=dev).repeat(B // 8, 1, 1, 1).contiguous()
         out = torch.empty_like(x)
         npix, bpp = B * H * W, 2 * 3 * x.element_size()
         ref_sums = ops.lab_moments(natural_frames(1, H, W, seed=9, dtype=dt, device=dev))
@@ -79,6 +79,9 @@ def rows_cm():
             full.recompute = True
             report(f"full_chain_g_cm_l_u/{tag}/recompute_G{g}", timeit(lambda: full(x, out=out)), npix, bpp)
             full.recompute = False
+        full.group_frames, full.serial = 0, True
+        report(f"full_chain_g_cm_l_u/{tag}/serial", timeit(lambda: full(x, out=out)), npix, bpp)
+        full.serial = False
         full.group_frames, full.split = 0, True
         report(f"full_chain_g_cm_l_u/{tag}/three_calls", timeit(lambda: full(x, out=out)), npix, bpp)
         full.split = False
