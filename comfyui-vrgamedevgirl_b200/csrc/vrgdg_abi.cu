@@ -111,9 +111,11 @@ bool build_tmap(CUtensorMap* map, const void* in, int B, int H, int RW, int dtyp
 }
 
 size_t lut_cells_floats(int S) { return (size_t)S * S * S * LUT_CELL_FLOATS; }
+// packed table = corner cells (96 B per node) followed by the polynomial cells of the fast chains (96 B per node, vrgdg_math.cuh)
 
 void fill_lut(LutParams& L, const float* lut, int S, const float* dmin, const float* dspan, float blend, float omb) {
   L.lut = lut; L.S = S; L.smax = (float)(S - 1);
+  L.lutp = lut + lut_cells_floats(S);
   for (int i = 0; i < 3; ++i) { L.dmin[i] = dmin[i]; L.dspan[i] = dspan[i]; }
   L.blend = blend; L.one_minus_blend = omb;
   L.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f) ? 1 : 0;
@@ -175,7 +177,7 @@ int vrgdg_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int64_t vrgdg_lut3d_packed_bytes(int lut_size) {
   if (lut_size < 2 || lut_size > 256) return 0;
-  return (int64_t)lut_cells_floats(lut_size) * 4;
+  return (int64_t)lut_cells_floats(lut_size) * 2 * 4;
 }
 
 int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream) {
@@ -187,6 +189,8 @@ int vrgdg_lut3d_pack(const float* lut, float* packed, int lut_size, void* stream
   if (rc) return rc;
   const int n = lut_size * lut_size * lut_size;
   k_lut_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed, lut_size);
+  count_launch();
+  k_lutp_pack<<<(n + 255) / 256, 256, 0, ctx.stream>>>(lut, packed + lut_cells_floats(lut_size), lut_size);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "vrgdg_lut3d_pack");

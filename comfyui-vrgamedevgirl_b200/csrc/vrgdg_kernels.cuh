@@ -81,6 +81,10 @@ struct PointParams {
   LutParams lut;
 };
 
+#ifndef VRGDG_LUT_POLY
+#define VRGDG_LUT_POLY 1             // 0: the fast chains interpolate the corner cells too (A/B switch of tools/build_variant.sh)
+#endif
+
 // One pixel through the enabled stages; (zr,zg,zb) = this pixel's N(0,1) triple (generator or external).
 template <int MASK, bool EXACT>
 __device__ __forceinline__ void process_pixel(const PointParams& P, const CmFold& cmf, float zr, float zg, float zb,
@@ -97,7 +101,8 @@ __device__ __forceinline__ void process_pixel(const PointParams& P, const CmFold
   }
   if (MASK & ST_LUT) {
     float x0 = r, x1 = g, x2 = b;
-    lut3d_eval<EXACT>(P.lut, r, g, b);
+    if (EXACT || !VRGDG_LUT_POLY) lut3d_eval<EXACT>(P.lut, r, g, b);
+    else lutp_eval(P.lut, r, g, b);                  // fast arithmetic: polynomial cells, 7 FMAs per channel
     if (P.lut.blend < 1.0f) {
       r = lut_blend<EXACT>(x0, r, P.lut.blend, P.lut.one_minus_blend);
       g = lut_blend<EXACT>(x1, g, P.lut.blend, P.lut.one_minus_blend);
@@ -113,7 +118,8 @@ __device__ __forceinline__ void process_pair(const PointParams& P, const CmFold&
   process_pixel<(MASK & ~ST_LUT), EXACT>(P, cmf, z[3], z[4], z[5], p[3], p[4], p[5]);
   if (MASK & ST_LUT) {
     float x[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
-    lut3d_eval2<EXACT>(P.lut, p, p + 3);
+    if (EXACT || !VRGDG_LUT_POLY) lut3d_eval2<EXACT>(P.lut, p, p + 3);
+    else lutp_eval2(P.lut, p, p + 3);
     if (P.lut.blend < 1.0f) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) p[i] = lut_blend<EXACT>(x[i], p[i], P.lut.blend, P.lut.one_minus_blend);
@@ -666,8 +672,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
 #define VRGDG_EARLY_REFILL 1
 #endif
   constexpr bool EARLY = WORK && (VRGDG_EARLY_REFILL != 0);
-  constexpr uint32_t AHEAD = EARLY ? NS : NS - 1;
-  static_assert(AHEAD >= 1, "a single stage needs the early refill");
+  // a single in-place stage (NS == 1 without a work tile) is refilled at the END of the iteration, once the stencil has read it;
+  // the load latency is then covered by the other resident CTAs of the SM instead of a second stage
+  constexpr bool LATE1 = !EARLY && NS == 1;
+  constexpr uint32_t AHEAD = EARLY ? NS : (LATE1 ? 1 : NS - 1);
   if (tma && tid == 0) {
     for (uint32_t k = 0; k < AHEAD && k < n_my; ++k) issue(k);
   }
@@ -679,7 +687,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     T* raw = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(stage0) + (size_t)s * C::STAGE_BYTES);
 
     if (tma) {
-      if (!EARLY && tid == 0 && k + NS - 1 < n_my) {
+      if (!EARLY && !LATE1 && tid == 0 && k + NS - 1 < n_my) {
         fence_proxy_async();          // order earlier generic-proxy accesses of that stage before the async write
         issue(k + NS - 1);
       }
@@ -799,6 +807,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __
     }
     if (tma) fence_proxy_async();   // generic-proxy writes to this stage happen-before its next async refill
     __syncthreads();   // every thread is done with this stage before it is refilled
+    if (LATE1 && tma && tid == 0 && k + 1 < n_my) issue(k + 1);
   }
 }
 
@@ -978,6 +987,20 @@ k_lut_pack(const float* __restrict__ lut3, float* __restrict__ cells, int S) {
     const int r = i % S, g = (i / S) % S, b = i / (S * S);
     float e[LUT_CELL_FLOATS];
     lut_pack_entry(lut3, S, b, g, r, e);
+    float4* d = reinterpret_cast<float4*>(cells + (size_t)i * LUT_CELL_FLOATS);
+#pragma unroll
+    for (int k = 0; k < LUT_CELL_FLOATS / 4; ++k) d[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+  }
+}
+
+// polynomial cell table of the fast chains (vrgdg_math.cuh "polynomial cells")
+static __global__ void __launch_bounds__(256)
+k_lutp_pack(const float* __restrict__ lut3, float* __restrict__ cells, int S) {
+  const int n = S * S * S;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int r = i % S, g = (i / S) % S, b = i / (S * S);
+    float e[LUT_CELL_FLOATS];
+    lutp_pack_entry(lut3, S, b, g, r, e);
     float4* d = reinterpret_cast<float4*>(cells + (size_t)i * LUT_CELL_FLOATS);
 #pragma unroll
     for (int k = 0; k < LUT_CELL_FLOATS / 4; ++k) d[k] = make_float4(e[4 * k], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);

@@ -228,6 +228,7 @@ VRGDG_HD void grain_blend_fast(float& r, float& g, float& b, float zr, float zg,
 // 32-byte r-pair table = 60-65 Gpx/s on grained frames, 3 lookups/px with this layout = 73-84 Gpx/s, 24 scalar = 34).
 struct LutParams {
   const float* lut;      // cell table, S*S*S*24 floats: per cell three 32-byte sectors (R, G, B), 8 corners each
+  const float* lutp;     // polynomial cell table (fast arithmetic only, see lutp_* below), same shape as `lut`
   int S;
   float smax;            // float(S-1)
   float dmin[3], dspan[3];
@@ -354,6 +355,59 @@ VRGDG_HD void lut3d_eval2(const LutParams& P, float* a, float* b) {
   const F8 b0 = lut_load8(cb.p), b1 = lut_load8(cb.p + 8), b2 = lut_load8(cb.p + 16);
   lut_finish<EXACT>(ca, a0, a1, a2, a[0], a[1], a[2]);
   lut_finish<EXACT>(cb, b0, b1, b2, b[0], b[1], b[2]);
+}
+
+// ---- polynomial cells (fast arithmetic only) ----------------------------------------------------------
+// The chains that draw their own grain run contracted arithmetic anyway (tolerance 1e-5), so their lookup reads a second table
+// that holds, per cell and channel, the COEFFICIENTS of the trilinear polynomial instead of its corner values:
+//   v(fr, fg, fb) = sum over X,Y,Z in {0,1} of k_XYZ fr^X fg^Y fb^Z,
+//   k_000 = c000, k_100 = c100 - c000, k_010 = c010 - c000, k_110 = c110 - c100 - c010 + c000, ...  (differences along r, g, b)
+// evaluated as a nested Horner form with 7 FMAs per channel (the corner form needs 7 lerps = 14 instructions):
+//   v = (k000 + fb k001 + fg (k010 + fb k011)) + fr (k100 + fb k101 + fg (k110 + fb k111)).
+// Same 96-byte channel-planar cell, coefficient k_XYZ in the slot of corner cXYZ; three 256-bit loads per pixel as before.
+// The coefficients are formed in double from the fp32 corners and rounded once; cell index and fractions are the exact path's.
+// Difference to the exact interpolation: a few 1e-8 of the table values (rounding of coefficients and FMAs).
+VRGDG_HD void lutp_pack_entry(const float* lut3, int S, int b, int g, int r, float* dst24) {
+  float c[LUT_CELL_FLOATS];
+  lut_pack_entry(lut3, S, b, g, r, c);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    double k[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k[i] = (double)c[8 * ch + i];
+#pragma unroll
+    for (int bit = 1; bit < 8; bit <<= 1) {          // Moebius transform: slot i (bit set) -= slot i without that bit
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i & bit) k[i] -= k[i ^ bit];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst24[8 * ch + i] = (float)k[i];
+  }
+}
+
+// one channel from its coefficient sector q (slot XYZ: X = r, Y = g, Z = b exponent; slot index = X + 2 Y + 4 Z)
+VRGDG_HD float lutp_channel(const F8& q, float fr, float fg, float fb) {
+  const float a0 = fmaf(fb, q.v[4], q.v[0]), b0 = fmaf(fb, q.v[5], q.v[1]);
+  const float a1 = fmaf(fb, q.v[6], q.v[2]), b1 = fmaf(fb, q.v[7], q.v[3]);
+  return clamp01(fmaf(fr, fmaf(fg, b1, b0), fmaf(fg, a1, a0)));
+}
+
+VRGDG_HD LutCell lutp_locate(const LutParams& P, float r, float g, float b) {
+  LutCell c = lut_locate(P, r, g, b);
+  c.p = P.lutp + (c.p - P.lut);
+  return c;
+}
+VRGDG_HD void lutp_eval(const LutParams& P, float& r, float& g, float& b) {
+  const LutCell c = lutp_locate(P, r, g, b);
+  const F8 q0 = lut_load8(c.p), q1 = lut_load8(c.p + 8), q2 = lut_load8(c.p + 16);
+  r = lutp_channel(q0, c.fr, c.fg, c.fb); g = lutp_channel(q1, c.fr, c.fg, c.fb); b = lutp_channel(q2, c.fr, c.fg, c.fb);
+}
+VRGDG_HD void lutp_eval2(const LutParams& P, float* a, float* b) {
+  const LutCell ca = lutp_locate(P, a[0], a[1], a[2]), cb = lutp_locate(P, b[0], b[1], b[2]);
+  const F8 a0 = lut_load8(ca.p), a1 = lut_load8(ca.p + 8), a2 = lut_load8(ca.p + 16);
+  const F8 b0 = lut_load8(cb.p), b1 = lut_load8(cb.p + 8), b2 = lut_load8(cb.p + 16);
+  a[0] = lutp_channel(a0, ca.fr, ca.fg, ca.fb); a[1] = lutp_channel(a1, ca.fr, ca.fg, ca.fb); a[2] = lutp_channel(a2, ca.fr, ca.fg, ca.fb);
+  b[0] = lutp_channel(b0, cb.fr, cb.fg, cb.fb); b[1] = lutp_channel(b1, cb.fr, cb.fg, cb.fb); b[2] = lutp_channel(b2, cb.fr, cb.fg, cb.fb);
 }
 
 // strength blend of apply_lut (:355-359) on already-rounded LUT output `y` and input `x`

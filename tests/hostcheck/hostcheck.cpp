@@ -58,10 +58,19 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
   for (int i = 0; i < 3; ++i) { P.dmin[i] = dmin[i]; P.dspan[i] = dspan[i]; }
   P.blend = blend; P.one_minus_blend = omb;
   P.unit_domain = (dmin[0] == 0.f && dmin[1] == 0.f && dmin[2] == 0.f && dspan[0] == 1.f && dspan[1] == 1.f && dspan[2] == 1.f);
+  // polynomial cells (fast arithmetic of the chains): the same packing as k_lutp_pack
+  float* poly = nullptr;
+  if (exact == 4) {
+    poly = new float[(size_t)S * S * S * LUT_CELL_FLOATS];
+    for (int bb = 0; bb < S; ++bb) for (int gg = 0; gg < S; ++gg) for (int rr = 0; rr < S; ++rr)
+      lutp_pack_entry(lut, S, bb, gg, rr, poly + ((size_t)(bb * S + gg) * S + rr) * LUT_CELL_FLOATS);
+    P.lutp = poly;
+  }
   for (int64_t i = 0; i < n; ++i) {
     float r = in[3 * i], g = in[3 * i + 1], b = in[3 * i + 2];
     float x0 = r, x1 = g, x2 = b;
-    if (exact == 1) lut3d_eval<true>(P, r, g, b);
+    if (exact == 4) lutp_eval(P, r, g, b);
+    else if (exact == 1) lut3d_eval<true>(P, r, g, b);
     else if (exact == 2) {                                           // the two-pixel form the kernels use (pixel paired with itself)
       float a[3] = {r, g, b}, c[3] = {r, g, b};
       lut3d_eval2<true>(P, a, c);
@@ -71,12 +80,13 @@ void hc_lut3d(const float* in, float* out, int64_t n, const float* lut, int S, c
       r = o0; g = o1; b = o2;
     } else lut3d_eval<false>(P, r, g, b);
     if (blend < 1.0f) {
-      if (exact) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }
+      if (exact && exact != 4) { r = lut_blend<true>(x0, r, blend, omb); g = lut_blend<true>(x1, g, blend, omb); b = lut_blend<true>(x2, b, blend, omb); }
       else { r = lut_blend<false>(x0, r, blend, omb); g = lut_blend<false>(x1, g, blend, omb); b = lut_blend<false>(x2, b, blend, omb); }
     }
     out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
   }
   delete[] packed;
+  delete[] poly;
 }
 
 void hc_div_const(const float* in, float* out, int64_t n, int d) {

@@ -65,6 +65,61 @@ def test_lut_65_full_size_vs_oracle(pkg, cuda_device, oracle, tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------------
+# polynomial LUT cells of the fast chains (vrgdg_math.cuh "polynomial cells")
+# ------------------------------------------------------------------------------------------------------
+def _fast_chain_vs_oracle(pkg, oracle, cuda_device, lut_data, olut, x, z, strength=10.0):
+    nv = pkg._native
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), lut=dict(lut_data=lut_data, strength=strength),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5, border=nv.BORDER_REPLICATE), device=cuda_device)
+    ref = oracle.chain_grain_lut_unsharp(x, z, 0.04, 0.5, olut, strength, 0.5)
+    fast = chain(x.to(cuda_device), ext_noise=z.to(cuda_device), fast_math=True)        # contracted arithmetic + polynomial cells
+    exact = chain(x.to(cuda_device), ext_noise=z.to(cuda_device))                        # reference op sequence + corner cells
+    return maxdiff(fast, ref), maxdiff(exact, ref)
+
+
+@pytest.mark.parametrize("size", [33, 64, 65])
+def test_polynomial_lut_cells_fast_chain_vs_oracle(pkg, cuda_device, oracle, tmp_path, size):
+    """the benchmarked arithmetic (fast_math: the lookup evaluates the trilinear polynomial from its coefficient cells) against the
+    oracle composition on the reference's noise, for the table sizes the reference ships"""
+    x = natural_frames(2, 270, 480, seed=size)
+    z = torch.randn(x.shape, generator=torch.Generator().manual_seed(size + 1))
+    if size == 33:
+        path = os.path.join(LUTS, "B200 Vintage 33.cube")
+    else:
+        path = write_big_cube(str(tmp_path / ("big_%d.cube" % size)), size)
+    fast, exact = _fast_chain_vs_oracle(pkg, oracle, cuda_device, pkg.VRGDG_LUTS._parse_cube_file(path), oracle.parse_cube(path), x, z)
+    assert exact <= 2e-6 and fast <= 4e-6, (fast, exact)
+    fast, exact = _fast_chain_vs_oracle(pkg, oracle, cuda_device, pkg.VRGDG_LUTS._parse_cube_file(path), oracle.parse_cube(path), x, z, strength=3.5)
+    assert exact <= 2e-6 and fast <= 4e-6, (fast, exact)
+
+
+def test_polynomial_lut_cells_any_table_range(pkg, cuda_device, oracle):
+    """tables whose values leave [0,1], a constant channel and a non-unit input domain through the coefficient cells; the packed
+    buffer holds both tables (corner cells for the exact entry points, coefficient cells for the fast chains)"""
+    S = 17
+    g = torch.Generator().manual_seed(5)
+    ax = torch.linspace(0, 1, S)
+    bb, gg, rr = torch.meshgrid(ax, ax, ax, indexing="ij")
+    lut = torch.stack([rr * 2.5 - 0.75 + 0.05 * torch.rand(rr.shape, generator=g),          # range ~[-0.75, 1.8]
+                       torch.full_like(gg, 0.25),                                              # constant channel
+                       0.4 + 0.2 * bb * gg], dim=-1).float().contiguous()                      # narrow range
+    data = dict(lut=lut, size=S, domain_min=torch.tensor([0.1, 0.0, 0.05]), domain_max=torch.tensor([0.9, 1.0, 0.8]), title="range")
+    x = natural_frames(1, 128, 192, seed=7)
+    z = torch.randn(x.shape, generator=torch.Generator().manual_seed(8))
+    fast, exact = _fast_chain_vs_oracle(pkg, oracle, cuda_device, data, data, x, z)
+    assert exact <= 2e-6 and fast <= 4e-6, (fast, exact)
+    packed = pkg.ops.pack_lut(lut, cuda_device)
+    n = S ** 3
+    assert packed.data.numel() == n * 48
+    corner, poly = packed.data[:n * 24].reshape(n, 3, 8).cpu(), packed.data[n * 24:].reshape(n, 3, 8).cpu()
+    assert torch.equal(poly[:, :, 0], corner[:, :, 0])                                         # k000 = c000
+    assert torch.equal(poly[:, 1, 1:], torch.zeros(n, 7))                                      # constant channel: no gradient terms
+    want = (corner[:, :, 7].double() - corner[:, :, 6].double() - corner[:, :, 5].double() - corner[:, :, 3].double()
+            + corner[:, :, 4].double() + corner[:, :, 2].double() + corner[:, :, 1].double() - corner[:, :, 0].double())
+    assert torch.equal(poly[:, :, 7], want.float())                                            # k111, formed in double, rounded once
+
+
+# ------------------------------------------------------------------------------------------------------
 # 16-bit frames against the oracle on the up-cast input
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])

@@ -103,6 +103,13 @@ def test_lut_eval_exact_is_bit_identical(hostcheck, oracle):
         assert np.array_equal(o, flat(g[f"{key}__s10"])), fname
         hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), blend, 1.0 - blend, 3)   # one channel per lane (tile kernels)
         assert np.array_equal(o, flat(g[f"{key}__s3p5"])), fname
+        # polynomial cells of the fast chains (trilinear coefficients, 7 FMAs per channel): same cell and weights, values within
+        # a few 1e-7 of the exact interpolation
+        rng = max(1.0, float(lut.max() - lut.min()))
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), 1.0, 0.0, 4)
+        assert np.abs(o - flat(g[f"{key}__s10"])).max() <= 5.0e-7 * rng, (fname, np.abs(o - flat(g[f"{key}__s10"])).max())
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), d["size"], P(dmin), P(span), blend, 1.0 - blend, 4)
+        assert np.abs(o - flat(g[f"{key}__s3p5"])).max() <= 5.0e-7 * rng, fname
 
 
 def test_stencil_epilogues_and_colormatch_within_tolerance(hostcheck, oracle):
