@@ -51,6 +51,14 @@ def _pin_result(src, nbytes):
     return 0 < nbytes <= limit
 
 
+def _env_bytes(name, default):
+    import os
+    try:
+        return int(os.environ.get(name, str(default)))
+    except ValueError:
+        return default
+
+
 def _side_streams(dev):
     """(upload, download) streams of a device, created once (stream creation is not free and ComfyUI calls nodes repeatedly)."""
     key = (dev.type, dev.index)
@@ -108,6 +116,22 @@ def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
         return torch.empty_like(src, device=out_device)
     src = src.contiguous()
     to_cpu = out_device.type == "cpu"
+    # Host frames move in pipeline chunks of at most VRGDG_STREAM_CHUNK_BYTES (default 256 MiB, at least one frame): a chunk as large
+    # as the batch would serialise upload, kernels and download.  Every caller's fn is independent of how the batch is cut (noise is
+    # keyed by the absolute frame index, statistics are per frame, temporal neighbours are fetched by index).
+    cap = _env_bytes("VRGDG_STREAM_CHUNK_BYTES", 256 << 20)
+    if cap > 0:
+        frame_bytes = max(1, src[0].numel() * src.element_size())
+        chunk = max(1, min(chunk, cap // frame_bytes))
+    # A pageable source is staged through two pinned buffers by a multi-threaded host copy (torch's CPU copy_), so the DMA engine
+    # reads pinned memory at PCIe speed while the next chunk is staged; the driver's own pageable path is a single-threaded bounce copy.
+    stage = None
+    if not src.is_pinned() and _env_bytes("VRGDG_STAGE_PAGEABLE", 1) > 0:
+        try:
+            stage = [torch.empty((chunk,) + tuple(src.shape[1:]), dtype=src.dtype, pin_memory=True) for _ in range(2)]
+        except RuntimeError:
+            stage = None                         # no pinned memory to spare: the driver's pageable path still works
+    stage_free = [None, None]
     with torch.cuda.device(dev):
         compute = torch.cuda.current_stream(dev)
         up, down = _side_streams(dev)
@@ -124,12 +148,21 @@ def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
         slot_free = [None] * len(slots)         # event: the kernels that read this slot have finished
         for ci, i in enumerate(range(0, B, chunk)):
             s, n = ci % len(slots), min(chunk, B - i)
+            host = src[i:i + n]
+            if stage is not None:
+                h = ci % 2
+                if stage_free[h] is not None:
+                    stage_free[h].synchronize()  # the upload that read this staging buffer two chunks ago has finished
+                stage[h][:n].copy_(host)
+                host = stage[h][:n]
             with torch.cuda.stream(up):
                 if slot_free[s] is not None:
                     up.wait_event(slot_free[s])
-                slots[s][:n].copy_(src[i:i + n], non_blocking=True)
+                slots[s][:n].copy_(host, non_blocking=True)
                 ev_up = torch.cuda.Event()
                 ev_up.record(up)
+            if stage is not None:
+                stage_free[ci % 2] = ev_up
             compute.wait_event(ev_up)
             d_out = fn(slots[s][:n], i)
             ev_done = torch.cuda.Event()

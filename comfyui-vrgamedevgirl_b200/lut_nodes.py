@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._runtime import compute_device
+from ._runtime import compute_device, stream_frames
 
 LUTS_DIR = os.path.join(os.path.dirname(__file__), "LUTS")
 SUPPORTED_LUT_EXTENSIONS = (".cube",)
@@ -134,8 +134,11 @@ def _run_lut(image, lut_data, strength):
     dmax = lut_data["domain_max"].to(dtype=work.dtype)
     span = torch.clamp(dmax - dmin, min=1e-6)
     lut_dev = _device_lut(lut_data, dev)
-    out = ops.lut3d_apply(work.to(dev), lut_dev, dmin.float().tolist(), span.float().tolist(), blend, 1.0 - blend)
-    return out.to(device=image.device)
+    lo, sp = dmin.float().tolist(), span.float().tolist()
+    if work.device.type == "cuda":
+        return ops.lut3d_apply(work.to(dev), lut_dev, lo, sp, blend, 1.0 - blend).to(device=image.device)
+    # host frames: the three-stream pipeline of the other nodes (chunked upload / lookup / download, pinned result)
+    return stream_frames(work, lambda f, i: ops.lut3d_apply(f, lut_dev, lo, sp, blend, 1.0 - blend), 0, image.device, dev)
 
 
 def _device_lut(lut_data, dev):

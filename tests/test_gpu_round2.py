@@ -309,6 +309,36 @@ def test_stream_frames_chunks_cuda_inputs_too(pkg, cuda_device):
         calls.clear()
         out = rt.stream_frames(src, fn, 1, torch.device("cpu"), cuda_device, depth=2)
         assert [c[1] for c in calls] == [0, 1, 2, 3, 4] and torch.equal(out, src * 0.5)
+        assert out.is_pinned()                                       # small host results are pinned: the next node uploads at PCIe speed
+
+
+def test_stream_frames_byte_cap_and_pageable_staging(pkg, cuda_device, monkeypatch):
+    """host batches are cut into pipeline chunks of at most VRGDG_STREAM_CHUNK_BYTES whatever the caller's chunk is; pageable sources
+    go through the pinned staging ring; the LUT node streams host frames like the other nodes (pinned result)"""
+    rt = __import__("importlib").import_module(pkg.__name__ + "._runtime")
+    x = natural_frames(7, 24, 32, seed=3)
+    frame_bytes = x[0].numel() * 4
+    calls = []
+
+    def fn(frames, first):
+        calls.append((int(frames.shape[0]), int(first)))
+        return frames + 0.25
+    monkeypatch.setenv("VRGDG_STREAM_CHUNK_BYTES", str(2 * frame_bytes + 5))
+    for stage in ("1", "0"):
+        monkeypatch.setenv("VRGDG_STAGE_PAGEABLE", stage)
+        calls.clear()
+        out = rt.stream_frames(x, fn, 0, torch.device("cpu"), cuda_device)
+        assert calls == [(2, 0), (2, 2), (2, 4), (1, 6)] and torch.equal(out, x + 0.25)
+    monkeypatch.setenv("VRGDG_STREAM_CHUNK_BYTES", "0")             # cap off: the caller's chunk stands
+    calls.clear()
+    out = rt.stream_frames(x, fn, 0, torch.device("cpu"), cuda_device)
+    assert calls == [(7, 0)] and torch.equal(out, x + 0.25)
+    monkeypatch.delenv("VRGDG_STREAM_CHUNK_BYTES")
+    monkeypatch.delenv("VRGDG_STAGE_PAGEABLE")
+    lut = _lut33(pkg)
+    node_out = pkg.VRGDG_LUTS().apply_lut(x, "B200 Vintage 33.cube", "auto", 10.0)[0]
+    dev_out = pkg.VRGDG_LUTS._apply_cube_lut(x.to(cuda_device), lut["lut"], lut["domain_min"], lut["domain_max"]).cpu()
+    assert node_out.device.type == "cpu" and node_out.is_pinned() and torch.equal(node_out, dev_out)
 
 
 # ------------------------------------------------------------------------------------------------------
