@@ -354,6 +354,16 @@ template <typename T, int MASK> struct TileCfg {
 #define VRGDG_HEAVY_THREADS 256
 #endif
   static constexpr int THREADS = HEAVY ? VRGDG_HEAVY_THREADS : 256;
+  // Register budget of the LUT configurations on fp32 frames: declaring a larger block than is ever launched lowers ptxas' register
+  // cap (65536 / (LB_THREADS * MINB)) below the 128 that two 256-thread CTAs would allow, which leaves room in the register file for
+  // the statistics blocks of the NEXT frame group next to two resident tile CTAs (pipelined colour-match schedule, vrgdg_abi.cu).
+  // Measured on the headline chain (64 x 4K fp32, profiles/r02_s2/pipe_sweep.jsonl): 256 (104-109 registers, one 128-thread statistics
+  // block fits beside two tile CTAs) 51.5 GPx/s, 320 (91-94 registers, two blocks) 55.0, 352 (80 registers + 20 bytes of spills, three
+  // blocks) 56.1; the tile kernel alone loses 0.6 % (fused grain + LUT + unsharp) to 3.7 % (serial colour-match chain) at 80 registers.
+#ifndef VRGDG_HEAVY_LB
+#define VRGDG_HEAVY_LB 352
+#endif
+  static constexpr int LB_THREADS = (HEAVY && sizeof(T) == 4 && VRGDG_HEAVY_LB > THREADS) ? VRGDG_HEAVY_LB : THREADS;
 #ifndef VRGDG_HEAVY_MINB
 #define VRGDG_HEAVY_MINB 2
 #endif
@@ -615,7 +625,7 @@ __device__ __forceinline__ void pair_store6(float* p, bool word0, const float* e
 }
 
 template <typename T, int MASK, bool EXACT>
-__global__ void __launch_bounds__((TileCfg<T, MASK>::THREADS), (TileCfg<T, MASK>::MINB))
+__global__ void __launch_bounds__((TileCfg<T, MASK>::LB_THREADS), (TileCfg<T, MASK>::MINB))
 k_tile(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ in, T* __restrict__ out, TileParams Q) {
   using C = TileCfg<T, MASK>;
   constexpr int NT = C::THREADS;
@@ -842,8 +852,13 @@ __device__ __forceinline__ void moments_add(float& r, float& g, float& b, float*
 // ST_CMF second pass.
 // NT = 256 (two reduction units per block) or 128 (one: small enough to share an SM with two resident tile CTAs, see
 // vrgdg_chain_cm_apply's pipelined schedule).
+#ifndef VRGDG_MOMENT_SMALL_MINB
+#define VRGDG_MOMENT_SMALL_MINB 10     // 128-thread blocks per SM the register cap is computed for: 8 = 64 registers (three blocks fit beside two
+                                       // 80-register tile CTAs), 10 = 48 registers + 12 bytes of spills (four blocks): 54.2 -> 55.5 GPx/s on the headline chain
+#endif
+template <int NT> struct MomentLaunch { static constexpr int MINB = (NT == MOMENT_UNIT) ? VRGDG_MOMENT_SMALL_MINB : 1; };
 template <typename T, bool GRAIN, bool VEC, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (MomentLaunch<NT>::MINB))
 k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials, float* __restrict__ fplanes) {
   static_assert(NT % MOMENT_UNIT == 0, "whole reduction units per block");
   constexpr int UPB = NT / MOMENT_UNIT;                       // units per block
