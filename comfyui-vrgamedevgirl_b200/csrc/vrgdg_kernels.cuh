@@ -856,7 +856,7 @@ __device__ __forceinline__ void moments_add(float& r, float& g, float& b, float*
 #define VRGDG_MOMENT_SMALL_MINB 10     // 128-thread blocks per SM the register cap is computed for: 8 = 64 registers (three blocks fit beside two
                                        // 80-register tile CTAs), 10 = 48 registers + 12 bytes of spills (four blocks): 54.2 -> 55.5 GPx/s on the headline chain
 #endif
-template <int NT> struct MomentLaunch { static constexpr int MINB = (NT == MOMENT_UNIT) ? VRGDG_MOMENT_SMALL_MINB : 1; };
+template <int NT> struct MomentLaunch { static constexpr int MINB = (NT == MOMENT_UNIT) ? VRGDG_MOMENT_SMALL_MINB : 4; };   // 256 threads: 64 registers as before
 template <typename T, bool GRAIN, bool VEC, int NT>
 __global__ void __launch_bounds__(NT, (MomentLaunch<NT>::MINB))
 k_lab_moments(const T* __restrict__ in, PointParams P, int row0, int rows, double* __restrict__ partials, float* __restrict__ fplanes) {

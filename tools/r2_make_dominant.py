@@ -7,7 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-D = os.path.join(ROOT, "profiles", "r02_final")
+D = os.path.join(ROOT, "profiles", sys.argv[1] if len(sys.argv) > 1 else "r02_final2")
 src_hash = importlib.import_module("comfyui-vrgamedevgirl_b200.build")._source_hash()
 
 
@@ -29,7 +29,7 @@ out = {
                       "k_lab_moments<float,1,1>": {"dram_read": mom["dram_read_bytes"], "dram_write": mom["dram_write_bytes"], "duration_us": mom["duration_us"],
                                                   "grid": mom["grid"], "block": mom["block"]}},
         "algorithmic_bytes_per_step": 128 * 2160 * 3840 * 24,
-        "capture": "profiles/r02_final/ncu_apply_f32_* + ncu_momstore_f32_* (tools/r2_run8.sh)",
+        "capture": "profiles/%s/ncu_apply_f32_* + ncu_momstore_f32_* (tools/r2_run20.sh)" % os.path.basename(D) + "",
         "src_hash": src_hash,
     },
     "configs1_f16": {
@@ -37,7 +37,7 @@ out = {
         "dram_bytes_per_launch": int(c1["dram_read_bytes"] + c1["dram_write_bytes"]),
         "duration_us": c1["duration_us"], "grid": c1["grid"], "block": c1["block"], "dyn_smem_bytes": c1["dyn_smem_bytes"],
         "algorithmic_bytes_per_launch": 64 * 1080 * 1920 * 12,
-        "capture": "profiles/r02_final/ncu_configs1_f16_* (tools/r2_run8.sh)",
+        "capture": "profiles/%s/ncu_configs1_f16_* (tools/r2_run20.sh)" % os.path.basename(D) + "",
         "src_hash": src_hash,
     },
 }
