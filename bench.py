@@ -300,6 +300,9 @@ def run_b200(args):
     alt = {}
     if not args.no_extra:
         alt_steps = max(2, min(args.steps, 5))
+        chain.serial = True
+        alt["f_planes_serial_one_call_ms"], _ = timed(step, alt_steps, 1)    # same kernels one after the other: what the concurrent schedule hides
+        chain.serial = False
         chain.recompute = True
         alt["recompute_one_call_ms"], _ = timed(step, alt_steps, 1)          # pass 2 re-reads the frames, redraws the grain, repeats the forward Lab
         chain.split, chain.timing = True, []
@@ -440,7 +443,7 @@ def run_b200(args):
                            "the two passes of neighbouring frame groups run concurrently (pipelined schedule); HBM carries 48 B/px at ~0.4 of its "
                            "peak: see profiles/README.md",
                 "traffic": tr}), **(st or {})),
-            "schedules_ms_per_step": dict({"f_planes_one_call (headline)": round(ms_step, 4)}, **alt),
+            "schedules_ms_per_step": dict({"f_planes_pipelined_one_call (headline)": round(ms_step, 4)}, **alt),
             "e2e": {"value": round(e2e_value, 1), "unit": "MP/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
                     "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps, "frames_per_gpu": nE,
                     "api": "PostChain.run_host(pinned 4K fp32 frames, chunk_frames=%d), sub-batch of %d frames per GPU" % (chunk, nE),
