@@ -343,6 +343,32 @@ def run_b200(args):
             "value": round(world * n2 / 1e6 / (ms2 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms2, 4), "steps": ex_steps,
             "roofline": roofline(n2 * 12, ms2, dict({"kernel": "k_tile<half, grain|lut>", "traffic": tr2}, **(st2 or {})))}
         del x2, o2, c4
+        # configs[2]: colour match alone on 4K fp32 frames (256 frames over 8 GPUs = 32 per GPU) against one reference frame, the reference
+        # statistics gathered over NCCL inside every step: (a) the reference's algorithm (LAB mean / std transfer, nodes.py:91-124),
+        # (b) the histogram / CDF mode BASELINE.json words it as (labelled extension, parity unpinned)
+        cm_only = pkg.chain.PostChain(colormatch=dict(ref_sums=vdist.reference_sums_distributed(ref), strength=1.0), device=dev)
+
+        def cm_step():
+            cm_only.set_reference(ref_sums=vdist.reference_sums_distributed(ref))
+            cm_only(x4, first_frame=first, out=o4)
+        ms3, _ = timed(cm_step, ex_steps, 3)
+        extras["configs2_colormatch_lab_4k_f32"] = {
+            "workload": "configs[2] per-GPU shard, the reference's LAB mean/std transfer: 32 x 3840x2160 fp32 frames per GPU vs one 4K reference frame "
+                        "(rows sharded, 56-byte all-gather per step), vrgdg_chain_cm_apply (statistics pass + f-planes, apply pass)",
+            "value": round(world * n4 / 1e6 / (ms3 / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms3, 4), "steps": ex_steps,
+            "roofline": roofline(n4 * 24, ms3, {"kernel": "k_lab_moments<float, store f-planes> + k_point<float, colormatch-from-f>", "moved_bytes_per_pixel": 48})}
+
+        def hist_step():
+            ref_counts = vdist.reference_histogram_distributed(ref)
+            tables = pkg.ops.histmatch_tables(pkg.ops.hist_counts(x4), ref_counts)
+            pkg.ops.histmatch_apply(x4, tables, 1.0, 0.0)
+        ms3h, _ = timed(hist_step, ex_steps, 3)
+        extras["configs2_colormatch_histogram_4k_f32"] = {
+            "workload": "configs[2] per-GPU shard, histogram / CDF transfer (extension without a reference counterpart; parity unpinned): 32 x 3840x2160 "
+                        "fp32 frames per GPU vs one 4K reference frame (rows sharded, all-gather of 3 x 256 counters per rank per step)",
+            "value": round(world * n4 / 1e6 / (ms3h / 1e3), 1), "unit": "MP/s", "ms_per_step": round(ms3h, 4), "steps": ex_steps,
+            "roofline": roofline(n4 * 24, ms3h, {"kernel": "k_hist_counts<float> + k_histmatch_tables + k_histmatch_apply<float>", "moved_bytes_per_pixel": 36})}
+        del cm_only
         # configs[4]: temporal 3-frame sharpen, 512 x 1080p fp32 frames over 4 GPUs = 128 frames per GPU (labelled extension:
         # the reference has no temporal operator); at N > 1 every step exchanges one halo frame per shard boundary (NCCL send/recv)
         x5 = tile_frames(device_natural_frames(8, 1080, 1920, seed=100 + rank, dtype=torch.float32, dev=dev), 128)
