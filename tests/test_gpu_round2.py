@@ -77,20 +77,38 @@ def _fast_chain_vs_oracle(pkg, oracle, cuda_device, lut_data, olut, x, z, streng
     return maxdiff(fast, ref), maxdiff(exact, ref)
 
 
-@pytest.mark.parametrize("size", [33, 64, 65])
+SHIPPED = {17: "Warm_Fade_17.cube", 25: "Teal_Orange_25.cube", 32: "Bleach_Bypass_32.cube", 33: "B200 Vintage 33.cube"}
+
+
+@pytest.mark.parametrize("size", [17, 25, 32, 33, 64, 65])
 def test_polynomial_lut_cells_fast_chain_vs_oracle(pkg, cuda_device, oracle, tmp_path, size):
     """the benchmarked arithmetic (fast_math: the lookup evaluates the trilinear polynomial from its coefficient cells) against the
-    oracle composition on the reference's noise, for the table sizes the reference ships"""
+    oracle composition on the reference's noise, for every table size the reference ships (25, 32, 33, 64, 65) and 17"""
     x = natural_frames(2, 270, 480, seed=size)
     z = torch.randn(x.shape, generator=torch.Generator().manual_seed(size + 1))
-    if size == 33:
-        path = os.path.join(LUTS, "B200 Vintage 33.cube")
+    if size in SHIPPED:
+        path = os.path.join(LUTS, SHIPPED[size])
     else:
         path = write_big_cube(str(tmp_path / ("big_%d.cube" % size)), size)
     fast, exact = _fast_chain_vs_oracle(pkg, oracle, cuda_device, pkg.VRGDG_LUTS._parse_cube_file(path), oracle.parse_cube(path), x, z)
     assert exact <= 2e-6 and fast <= 4e-6, (fast, exact)
     fast, exact = _fast_chain_vs_oracle(pkg, oracle, cuda_device, pkg.VRGDG_LUTS._parse_cube_file(path), oracle.parse_cube(path), x, z, strength=3.5)
     assert exact <= 2e-6 and fast <= 4e-6, (fast, exact)
+
+
+def test_polynomial_lut_cells_whole_4k_frame_fast_equals_exact(pkg, cuda_device):
+    """BASELINE size: one whole 3840x2160 fp32 frame through the fused chain on the same external noise, benchmarked arithmetic
+    (coefficient cells, contracted FMAs, fast stencil) against the reference op sequence (corner cells), which the small-size tests
+    pin to the oracle; every pixel within 4e-6"""
+    nv = pkg._native
+    x = natural_frames(1, 2160, 3840, seed=4, device=cuda_device)
+    z = torch.randn(x.shape, generator=torch.Generator(device=cuda_device).manual_seed(5), device=cuda_device)
+    chain = pkg.chain.PostChain(grain=dict(intensity=0.04, saturation_mix=0.5, seed=0), lut=dict(lut_data=_lut33(pkg), strength=10.0),
+                                stencil=dict(op=nv.STENCIL_BOX_UNSHARP, strength=0.5, border=nv.BORDER_REPLICATE), device=cuda_device)
+    fast, exact = chain(x, ext_noise=z, fast_math=True), chain(x, ext_noise=z)
+    assert nv.last_tile_path() == "tma"
+    assert float((fast - exact).abs().max()) <= 4e-6
+    assert float(fast.min()) >= 0.0 and float(fast.max()) <= 1.0
 
 
 def test_polynomial_lut_cells_any_table_range(pkg, cuda_device, oracle):
