@@ -59,6 +59,15 @@ def _env_bytes(name, default):
         return default
 
 
+def pipeline_chunk(chunk, frame_bytes, cap=None):
+    """Frames per pipeline chunk for host sources: the caller's chunk, cut down to VRGDG_STREAM_CHUNK_BYTES (default 256 MiB; 0 = no
+    cap), never below one frame."""
+    cap = _env_bytes("VRGDG_STREAM_CHUNK_BYTES", 256 << 20) if cap is None else int(cap)
+    if cap <= 0:
+        return max(1, int(chunk))
+    return max(1, min(int(chunk), cap // max(1, int(frame_bytes))))
+
+
 def _side_streams(dev):
     """(upload, download) streams of a device, created once (stream creation is not free and ComfyUI calls nodes repeatedly)."""
     key = (dev.type, dev.index)
@@ -119,10 +128,7 @@ def stream_frames(src, fn, chunk, out_device, device=None, out=None, depth=2):
     # Host frames move in pipeline chunks of at most VRGDG_STREAM_CHUNK_BYTES (default 256 MiB, at least one frame): a chunk as large
     # as the batch would serialise upload, kernels and download.  Every caller's fn is independent of how the batch is cut (noise is
     # keyed by the absolute frame index, statistics are per frame, temporal neighbours are fetched by index).
-    cap = _env_bytes("VRGDG_STREAM_CHUNK_BYTES", 256 << 20)
-    if cap > 0:
-        frame_bytes = max(1, src[0].numel() * src.element_size())
-        chunk = max(1, min(chunk, cap // frame_bytes))
+    chunk = pipeline_chunk(chunk, src[0].numel() * src.element_size())
     # A pageable source is staged through two pinned buffers by a multi-threaded host copy (torch's CPU copy_), so the DMA engine
     # reads pinned memory at PCIe speed while the next chunk is staged; the driver's own pageable path is a single-threaded bounce copy.
     stage = None

@@ -278,3 +278,20 @@ def test_random_cube_files_and_lanczos_tables_fuzz(pkg, oracle, tmp_path):
         o2, c2 = oracle.lanczos4_tables(s_, d_)
         assert np.array_equal(ofs, o2) and np.array_equal(coef, c2), (s_, d_)
         assert int(np.abs(coef.astype(np.int32).sum(axis=1) - 2048).max()) <= 3     # weights sum to 1 in fixed point, up to rounding
+
+
+def test_pipeline_chunk_rule(pkg, monkeypatch):
+    """host batches are cut into pipeline chunks by BYTES whatever the node's batch widget says (results never depend on the cut);
+    the rule is a pure function of (caller's chunk, frame size, cap)"""
+    rt = __import__("importlib").import_module(pkg.__name__ + "._runtime")
+    frame_4k = 2160 * 3840 * 3 * 4
+    monkeypatch.delenv("VRGDG_STREAM_CHUNK_BYTES", raising=False)
+    assert rt.pipeline_chunk(16, frame_4k) == 2                      # 256 MiB / 99.5 MB
+    assert rt.pipeline_chunk(1, frame_4k) == 1                       # the caller's smaller chunk stands
+    assert rt.pipeline_chunk(500, 1920 * 1080 * 3 * 2) == 21         # 1080p fp16
+    assert rt.pipeline_chunk(8, 1 << 30) == 1                        # a frame larger than the cap still moves, one at a time
+    assert rt.pipeline_chunk(8, frame_4k, cap=0) == 8                # cap off
+    monkeypatch.setenv("VRGDG_STREAM_CHUNK_BYTES", str(4 * frame_4k))
+    assert rt.pipeline_chunk(16, frame_4k) == 4
+    monkeypatch.setenv("VRGDG_STREAM_CHUNK_BYTES", "not a number")   # unreadable value: the default
+    assert rt.pipeline_chunk(16, frame_4k) == 2
