@@ -59,6 +59,20 @@ def _env_bytes(name, default):
         return default
 
 
+def upload(t, dev):
+    """One host tensor to the device.  Large pageable tensors (a 4K reference frame is 99.5 MB) go through a pinned staging buffer
+    filled by torch's multi-threaded host copy instead of the driver's single-threaded bounce copy; torch's host allocator keeps the
+    staging block alive until the copy has finished and caches it for the next call.  CUDA tensors and small ones: plain .to()."""
+    if t.device.type != "cpu" or t.is_pinned() or t.numel() * t.element_size() < (8 << 20) or _env_bytes("VRGDG_STAGE_PAGEABLE", 1) <= 0:
+        return t.to(dev)
+    try:
+        stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return t.to(dev)
+    stage.copy_(t)
+    return stage.to(dev, non_blocking=True)
+
+
 def pipeline_chunk(chunk, frame_bytes, cap=None):
     """Frames per pipeline chunk for host sources: the caller's chunk, cut down to VRGDG_STREAM_CHUNK_BYTES (default 256 MiB; 0 = no
     cap), never below one frame."""

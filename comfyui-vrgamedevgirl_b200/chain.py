@@ -11,7 +11,7 @@ import torch
 
 from . import _native as nv
 from . import ops
-from ._runtime import compute_device, stream_frames
+from ._runtime import compute_device, stream_frames, upload
 
 
 class PostChain:
@@ -41,7 +41,7 @@ class PostChain:
         if ref_sums is not None:
             self._ref_sums = ref_sums.to(self.device, torch.float64).reshape(-1, 7).contiguous()
         elif reference_image is not None:
-            self._ref_sums = ops.lab_moments(reference_image.to(self.device))
+            self._ref_sums = ops.lab_moments(upload(reference_image, self.device))
         else:
             raise ValueError("colour match needs reference_image or ref_sums")
 

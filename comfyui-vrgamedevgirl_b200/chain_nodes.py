@@ -10,7 +10,7 @@
 import torch
 
 from . import _native as nv
-from ._runtime import compute_device, result_device, stream_frames
+from ._runtime import compute_device, result_device, stream_frames, upload
 from .chain import PostChain
 from .filter_nodes import _as_frames, draw_seed
 from .lut_nodes import NO_LUTS, VRGDG_LUTS, _list_lut_files
@@ -150,7 +150,7 @@ class VRGDG_B200_HistogramColorMatch:
         dev = compute_device(images)
         t = float(match_strength)
         with torch.cuda.device(dev):
-            ref_counts = ops.hist_counts(ref.to(dev).to(images.dtype))
+            ref_counts = ops.hist_counts(upload(ref, dev).to(images.dtype))
 
         def run(frames, first):
             tables = ops.histmatch_tables(ops.hist_counts(frames), ref_counts)

@@ -10,7 +10,7 @@ import torch
 
 from . import _native as nv
 from . import ops
-from ._runtime import compute_device, result_device, stream_frames
+from ._runtime import compute_device, result_device, stream_frames, upload
 
 _FLOATS = (torch.float32, torch.float16, torch.bfloat16)
 
@@ -88,7 +88,7 @@ class ColorMatchToReference:
         dev = compute_device(images)
         t = float(match_strength)
         with torch.cuda.device(dev):
-            ref_sums = ops.lab_moments(reference_image.to(dev).to(images.dtype))
+            ref_sums = ops.lab_moments(upload(reference_image, dev).to(images.dtype))
         d = nv.ChainDesc()
         d.colormatch_enabled, d.cm_t, d.cm_one_minus_t = 1, t, 1.0 - t
         state = {"scratch": None}
