@@ -7,7 +7,7 @@ the context dict and the logging are the reference's control plane and stay out 
 """
 
 from . import ops
-from ._runtime import compute_device
+from ._runtime import compute_device, upload
 
 
 def _interpolation(mode):
@@ -41,7 +41,7 @@ def _resize_batch(images, target_width, target_height, fit_mode, resize_method, 
     if images.ndim != 4 or images.shape[0] < 1:
         raise ValueError("Video Enhance requires a non-empty IMAGE batch.")
     dev = compute_device(images)
-    src = images.to(dev)
+    src = upload(images, dev)
     x0, y0, sw, sh = _roi if _roi is not None else (0, 0, int(src.shape[2]), int(src.shape[1]))
     resampled, offset = _resize_plan(sw, sh, target_width, target_height, fit_mode)
     ow, oh = _output_size(resampled, offset, target_width, target_height, fit_mode)
@@ -65,8 +65,8 @@ def restore_frames(originals, enhanced, source_width, source_height, fit_mode, r
     """Tensor part of VRGDG_VideoEnhanceRestore.restore (:404-418): resample the enhanced frames back to the source size and lerp
     them over the originals; frames the sampler did not return keep the original (clamped)."""
     dev = compute_device(originals)
-    orig = originals.to(dev)
-    restored = _restore_batch(enhanced.to(dev), source_width, source_height, fit_mode, resize_method).to(orig.dtype)
+    orig = upload(originals, dev)
+    restored = _restore_batch(upload(enhanced, dev), source_width, source_height, fit_mode, resize_method).to(orig.dtype)
     usable = min(int(orig.shape[0]), int(restored.shape[0]))
     strength = float(enhancement_strength)
     output = orig.clamp(0, 1)

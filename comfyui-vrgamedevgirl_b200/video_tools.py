@@ -11,14 +11,14 @@ import torch
 
 from . import _native as nv
 from . import ops
-from ._runtime import compute_device
+from ._runtime import compute_device, upload
 from .chain import PostChain
 from .lut_nodes import VRGDG_LUTS, _run_lut
 
 
 def _to_cuda(t, device=None):
     dev = compute_device(t) if device in (None, "cpu", "auto") or str(device) == "cpu" else torch.device(device)
-    return t.to(dev), dev
+    return upload(t, dev), dev
 
 
 def _apply_lut_tensor(image_tensor, lut_name, strength, device):
@@ -117,7 +117,7 @@ def _resize_frames(frames, output_width, output_height):
     for shape, idx in todo.items():
         if len(shape) != 3 or shape[2] != 3 or frames[idx[0]].dtype != np.uint8:
             raise ValueError("vrgdg_b200: _resize_frames expects uint8 [H,W,3] frames, got %s %s" % (shape, frames[idx[0]].dtype))
-        batch = torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in idx])).to(dev)
+        batch = upload(torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in idx])), dev)
         out = ops.resize_lanczos4_u8(batch, output_height, output_width).cpu().numpy()
         for j, i in enumerate(idx):
             resized[i] = out[j]
@@ -177,7 +177,7 @@ def enhance_frames(frames, output_width, output_height, settings, frame_start=0)
         # mixed sizes are legal for the reference (cv2 resizes frame by frame): take the helper-by-helper route
         return _tensor_to_frames(_apply_effects_batch(_frames_to_tensor(_resize_frames(frames, output_width, output_height)), settings, frame_start))
     dev = compute_device()
-    batch = torch.from_numpy(np.stack([np.ascontiguousarray(f) for f in frames], axis=0)).to(dev)
+    batch = upload(torch.from_numpy(np.stack([np.ascontiguousarray(f) for f in frames], axis=0)), dev)
     if batch.shape[1] != output_height or batch.shape[2] != output_width:
         batch = ops.resize_lanczos4_u8(batch, output_height, output_width)
     use_gpu = bool(settings.get("use_gpu", True))
@@ -200,7 +200,7 @@ def _frames_to_tensor(frames, device=None):
     """uint8 BGR frames (list of [H,W,3] arrays) -> float RGB [B,H,W,3] on the GPU: x/255 with the channel swap fused."""
     stacked = torch.from_numpy(np.stack(frames, axis=0))
     dev = compute_device() if device is None else torch.device(device)
-    return ops.u8bgr_to_rgb(stacked.to(dev))
+    return ops.u8bgr_to_rgb(upload(stacked, dev))
 
 
 def _tensor_to_frames(tensor):
