@@ -9,11 +9,13 @@ unsharp(.5) on 128 x 3840x2160 fp32 frames per GPU, synthesised on the device (w
 One "step" = one pass of the chain over the rank's frames:
     reference moments (k_lab_moments on the rank's row shard + ONE NCCL all-gather of 56 bytes per rank, dist.py)
     -> vrgdg_chain_cm_apply, per group of 8 frames: k_lab_moments (grain drawn, forward Lab, statistics, (fx,fy,fz) planes stored)
-       -> k_moments_final -> k_colormatch_params -> k_tile (colour match from the planes + LUT + unsharp)
+       -> k_moments_final -> k_colormatch_params -> k_tile (colour match from the planes + LUT + unsharp);
+       the statistics pass of group g+1 runs concurrently with the apply pass of group g (two internal streams, split register file)
   value : MP/s, frames resident in HBM (CUDA events around K steps on the launching stream, max over ranks)
   e2e   : MP/s through the public API (PostChain.run_host) from pinned HOST frames to pinned HOST frames on a stated sub-batch,
           H2D and D2H copies inside the timed region; e2e.stock_nodes = the same chain as four unchanged ComfyUI nodes
-  extra : configs[1] (64 x 1080p fp16, grain + LUT + unsharp) and "grain + LUT + unsharp at 4K fp32", each with its own roofline
+  extra : configs[1] (64 x 1080p fp16, grain + LUT + unsharp), "grain + LUT + unsharp at 4K fp32", configs[2] (colour match alone: LAB
+          transfer and histogram mode, reference statistics gathered every step), configs[4] (temporal sharpen), each with its own roofline
   --impl reference : the reference's CPU path for the same chain (oracle port of the reference nodes; /root/reference
           does not exist on the GPU box) on all host cores, rank 0 only, bounded sample per step
 """
