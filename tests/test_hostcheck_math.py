@@ -206,3 +206,38 @@ def test_div_const_is_the_correctly_rounded_quotient(hostcheck):
     z = np.array([-0.0], dtype=np.float32)
     hostcheck.hc_div_const(P(z), P(o), 1, 9)
     assert o[0] == 0.0                                                      # value equal; the sign of zero is not preserved
+
+
+def test_coefficient_cells_random_tables_vs_float64_trilinear(hostcheck):
+    """the fast chains' lookup (coefficient cells, 7 FMAs per channel; same code as the kernels, compiled for the host) on RANDOM tables of
+    several sizes, value ranges and input domains against a float64 evaluation of the trilinear formula: the error stays within a few
+    fp32 roundings of the table range whatever the table looks like (no smoothness assumed), and cell index / fractions are shared with
+    the exact path (whose result is compared with the same float64 evaluation)"""
+    hostcheck.hc_lut3d.argtypes = [vp, vp, i64, vp, ci, vp, vp, f32, f32, ci]
+    rng = np.random.default_rng(20260924)
+    for S, lo, hi in ((2, 0.0, 1.0), (9, -0.5, 1.5), (17, 0.0, 1.0), (33, -2.0, 3.0)):
+        lut = rng.uniform(lo, hi, size=(S, S, S, 3)).astype(np.float32)
+        dmin = np.array([0.05, 0.0, -0.1], dtype=np.float32)
+        span = np.array([0.9, 1.0, 1.3], dtype=np.float32)
+        x = rng.uniform(-0.2, 1.2, size=(20000, 3)).astype(np.float32)
+        x[:64] = rng.integers(0, S, size=(64, 3)).astype(np.float32) / np.float32(S - 1) * span + dmin      # some points on the lattice
+        # float64 trilinear on the float32 coordinates the kernels form (division, clamp, scale in fp32: the index math is shared)
+        n = np.clip(((x - dmin) / span).astype(np.float32), np.float32(0), np.float32(1))
+        c = (n * np.float32(S - 1)).astype(np.float32)
+        i0 = np.floor(c).astype(np.int64)
+        i1 = np.minimum(i0 + 1, S - 1)
+        f = (c - i0.astype(np.float32)).astype(np.float64)
+        L = lut.astype(np.float64)
+        r0, g0, b0, r1, g1, b1 = i0[:, 0], i0[:, 1], i0[:, 2], i1[:, 0], i1[:, 1], i1[:, 2]
+        fr, fg, fb = f[:, 0:1], f[:, 1:2], f[:, 2:3]
+        c00 = L[b0, g0, r0] * (1 - fb) + L[b1, g0, r0] * fb
+        c01 = L[b0, g1, r0] * (1 - fb) + L[b1, g1, r0] * fb
+        c10 = L[b0, g0, r1] * (1 - fb) + L[b1, g0, r1] * fb
+        c11 = L[b0, g1, r1] * (1 - fb) + L[b1, g1, r1] * fb
+        want = np.clip((c00 * (1 - fg) + c01 * fg) * (1 - fr) + (c10 * (1 - fg) + c11 * fg) * fr, 0.0, 1.0)
+        o = np.zeros_like(x)
+        bound = 1.0e-6 * max(1.0, hi - lo)
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), S, P(dmin), P(span), 1.0, 0.0, 1)          # exact path (corner cells)
+        assert np.abs(o - want).max() <= bound, (S, "exact", np.abs(o - want).max())
+        hostcheck.hc_lut3d(P(x), P(o), x.shape[0], P(lut), S, P(dmin), P(span), 1.0, 0.0, 4)          # coefficient cells
+        assert np.abs(o - want).max() <= bound, (S, "coefficients", np.abs(o - want).max())
